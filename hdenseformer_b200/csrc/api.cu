@@ -1,0 +1,54 @@
+// Library-level entry points: init / error string / version.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+static int g_sm_count = 0;
+static int g_device = -1;
+
+void hdf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int hdf_sm_count_cached() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+extern "C" {
+
+const char* hdf_last_error_string(void) { return g_err; }
+
+int hdf_version(void) { return 100; }
+
+int hdf_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    hdf_set_error("hdf_init: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    return HDF_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    hdf_set_error("hdf_init: device %d out of range (0..%d)", device, count - 1);
+    return HDF_ERR_ARG;
+  }
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, device);
+  if (e != cudaSuccess) {
+    hdf_set_error("hdf_init: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return HDF_ERR_CUDA;
+  }
+  if (p.major != 10) {
+    hdf_set_error("hdf_init: device %d is sm_%d%d; libhdf_b200 is built for sm_100a (B200) only", device, p.major, p.minor);
+    return HDF_ERR_ARCH;
+  }
+  g_sm_count = p.multiProcessorCount;
+  g_device = device;
+  return HDF_OK;
+}
+
+int hdf_sm_count(void) { return g_sm_count; }
+
+}  // extern "C"

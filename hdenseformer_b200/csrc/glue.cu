@@ -1,0 +1,841 @@
+// Bandwidth-bound glue on channels-last activations [N, V=D*H*W, C] (channel stride "ld" so every
+// operand can be a channel slice of a pre-allocated concat buffer: SURVEY 2.1 K10 "no cat kernel"):
+// InstanceNorm statistics / apply(+ReLU)(+residual) / backward, 2x2x2 max-pool, trilinear x2,
+// 1x1x1 heads, layout conversion, axpy, column sums.  128-bit vectorised accesses, fp32 math,
+// fp64 cross-thread reduction of statistics.
+#include "common.cuh"
+
+namespace {
+
+template <typename T> struct VecOf { static constexpr int value = 4; };
+template <> struct VecOf<bf16> { static constexpr int value = 8; };
+
+template <typename T, int VEC> __device__ __forceinline__ void loadv(const T* p, float* o) {
+  if (VEC == 8) load8<T>(p, o);
+  else if (VEC == 4) load4<T>(p, o);
+  else o[0] = to_f(p[0]);
+}
+template <typename T, int VEC> __device__ __forceinline__ void storev(T* p, const float* o) {
+  if (VEC == 8) store8<T>(p, o);
+  else if (VEC == 4) store4<T>(p, o);
+  else p[0] = from_f<T>(o[0]);
+}
+
+template <typename T>
+bool can_vec(const void* p, long long ld, int C) {
+  const int v = VecOf<T>::value;
+  return (C % v == 0) && (ld % v == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
+// ---------------------------------------------------------------------------
+// generic per-(n,c) two-quantity reduction over V rows.
+// grid (chunks, N), block 256.  partial[n][chunk][2][C] (double)
+// ---------------------------------------------------------------------------
+template <typename T, int VEC, class F>
+__global__ void __launch_bounds__(256) rowreduce_kernel(F f, int V, int C, int rows_per_chunk, double* __restrict__ partial) {
+  extern __shared__ double smd[];  // [2][rows_per_iter][C]
+  const int cpv = C / VEC;
+  const int rpi = 256 / cpv;  // rows per iteration (>=1 guaranteed by host)
+  const int tid = threadIdx.x;
+  const int cg = tid % cpv, r = tid / cpv;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int v0 = chunk * rows_per_chunk;
+  const int v1 = min(V, v0 + rows_per_chunk);
+  float sa[VEC], sb[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sa[i] = sb[i] = 0.f;
+  if (r < rpi) {
+    for (int v = v0 + r; v < v1; v += rpi) {
+      float a[VEC], b[VEC];
+      f.template eval<VEC>(n, v, cg * VEC, a, b);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { sa[i] += a[i]; sb[i] += b[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      smd[(0 * rpi + r) * C + cg * VEC + i] = (double)sa[i];
+      smd[(1 * rpi + r) * C + cg * VEC + i] = (double)sb[i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += 256) {
+    const int q = i / C, c = i % C;
+    double s = 0.0;
+    for (int rr = 0; rr < rpi; ++rr) s += smd[(q * rpi + rr) * C + c];
+    partial[(((long long)n * gridDim.x + chunk) * 2 + q) * C + c] = s;
+  }
+}
+
+template <typename T>
+struct StatsF {
+  const T* y; long long ld; long long V;
+  template <int VEC> __device__ void eval(int n, int v, int c, float* a, float* b) const {
+    loadv<T, VEC>(y + ((long long)n * V + v) * ld + c, a);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) b[i] = a[i] * a[i];
+  }
+};
+
+template <typename T>
+struct InBwdF {
+  const T* dout; long long ldd; const T* y; long long ldy; long long V;
+  const float* mean; const float* rstd; const float* gamma; const float* beta; int C; int relu;
+  template <int VEC> __device__ void eval(int n, int v, int c, float* a, float* b) const {
+    float g[VEC], x[VEC];
+    loadv<T, VEC>(dout + ((long long)n * V + v) * ldd + c, g);
+    loadv<T, VEC>(y + ((long long)n * V + v) * ldy + c, x);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float xh = (x[i] - mean[n * C + c + i]) * rstd[n * C + c + i];
+      const float z = xh * (gamma ? gamma[c + i] : 1.f) + (beta ? beta[c + i] : 0.f);
+      const float dz = (!relu || z > 0.f) ? g[i] : 0.f;
+      a[i] = dz;
+      b[i] = dz * xh;
+    }
+  }
+};
+
+template <typename T>
+struct ColSumF {
+  const T* x; long long ld; long long V;
+  template <int VEC> __device__ void eval(int n, int v, int c, float* a, float* b) const {
+    loadv<T, VEC>(x + ((long long)n * V + v) * ld + c, a);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) b[i] = 0.f;
+  }
+};
+
+__global__ void stats_finalize_kernel(const double* __restrict__ partial, int chunks, int C, long long V, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd, int NC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const int n = i / C, c = i % C;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s += partial[(((long long)n * chunks + k) * 2 + 0) * C + c];
+    q += partial[(((long long)n * chunks + k) * 2 + 1) * C + c];
+  }
+  const double m = s / (double)V;
+  double var = q / (double)V - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void sums_finalize_kernel(const double* __restrict__ partial, int chunks, int C, float* __restrict__ s1,
+                                     float* __restrict__ s2, int NC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const int n = i / C, c = i % C;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s += partial[(((long long)n * chunks + k) * 2 + 0) * C + c];
+    q += partial[(((long long)n * chunks + k) * 2 + 1) * C + c];
+  }
+  s1[i] = (float)s;
+  if (s2) s2[i] = (float)q;
+}
+
+__global__ void colsum_finalize_kernel(const double* __restrict__ partial, int chunks, int C, float* __restrict__ out,
+                                       int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += partial[((long long)k * 2 + 0) * C + c];
+  out[c] = accumulate ? out[c] + (float)s : (float)s;
+}
+
+__global__ void in_param_grads_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int N, int C,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) { a += s2[n * C + c]; b += s1[n * C + c]; }
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + a : a;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + b : b;
+}
+
+int reduce_chunks(long long V, int N) {
+  // ~4 waves of CTAs, at least 1024 rows per chunk
+  long long c = (4 * 148 + N - 1) / N;
+  long long mx = V / 1024 > 0 ? V / 1024 : 1;
+  if (c > mx) c = mx;
+  return (int)(c < 1 ? 1 : c);
+}
+
+template <typename T, class F>
+int launch_rowreduce(F f, const void* p0, long long ld0, const void* p1, long long ld1, int N, long long V, int C,
+                     double* partial, int& chunks, cudaStream_t s, const char* name) {
+  chunks = reduce_chunks(V, N);
+  const int rpc = cdiv(V, chunks);
+  chunks = cdiv(V, rpc);
+  dim3 grid(chunks, N);
+  const bool vec = can_vec<T>(p0, ld0, C) && (p1 == nullptr || can_vec<T>(p1, ld1, C)) && (C / VecOf<T>::value) <= 256;
+  if (vec) {
+    constexpr int VEC = VecOf<T>::value;
+    const int rpi = 256 / (C / VEC);
+    const size_t smem = (size_t)2 * rpi * C * sizeof(double);
+    rowreduce_kernel<T, VEC, F><<<grid, 256, smem, s>>>(f, (int)V, C, rpc, partial);
+  } else {
+    HDF_REQUIRE(C <= 256, "%s: scalar path supports C <= 256 (C=%d)", name, C);
+    const int rpi = 256 / C;
+    const size_t smem = (size_t)2 * rpi * C * sizeof(double);
+    rowreduce_kernel<T, 1, F><<<grid, 256, smem, s>>>(f, (int)V, C, rpc, partial);
+  }
+  HDF_LAUNCH_CHECK(name);
+  return HDF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// elementwise kernels over [N, V, C] vectors
+// ---------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void in_apply_kernel(const T* __restrict__ y, long long ldy, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const T* __restrict__ res, long long ldr,
+                                T* __restrict__ out, long long ldo, long long V, int C, int relu, long long total) {
+  const int cpv = C / VEC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpv) * VEC;
+    const long long row = i / cpv;
+    const int n = (int)(row / V);
+    float x[VEC], r[VEC];
+    loadv<T, VEC>(y + row * ldy + c, x);
+    if (res) loadv<T, VEC>(res + row * ldr + c, r);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float z = (x[k] - mean[n * C + c + k]) * rstd[n * C + c + k];
+      z = z * (gamma ? gamma[c + k] : 1.f) + (beta ? beta[c + k] : 0.f);
+      if (relu) z = fmaxf(z, 0.f);
+      if (res) z += r[k];
+      x[k] = z;
+    }
+    storev<T, VEC>(out + row * ldo + c, x);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void in_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ y, long long ldy,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ s1, const float* __restrict__ s2, T* __restrict__ dy,
+                                    long long ldo, long long V, int C, int relu, long long total) {
+  const int cpv = C / VEC;
+  const float invV = 1.f / (float)V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpv) * VEC;
+    const long long row = i / cpv;
+    const int n = (int)(row / V);
+    float g[VEC], x[VEC];
+    loadv<T, VEC>(dout + row * ldd + c, g);
+    loadv<T, VEC>(y + row * ldy + c, x);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int nc = n * C + c + k;
+      const float rs = rstd[nc];
+      const float xh = (x[k] - mean[nc]) * rs;
+      const float gm = gamma ? gamma[c + k] : 1.f;
+      const float z = xh * gm + (beta ? beta[c + k] : 0.f);
+      const float dz = (!relu || z > 0.f) ? g[k] : 0.f;
+      x[k] = gm * rs * (dz - s1[nc] * invV - xh * s2[nc] * invV);
+    }
+    storev<T, VEC>(dy + row * ldo + c, x);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void add_kernel(T* __restrict__ dst, long long ldd, const T* __restrict__ src, long long lds, int C,
+                           long long total) {
+  const int cpv = C / VEC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpv) * VEC;
+    const long long row = i / cpv;
+    float a[VEC], b[VEC];
+    loadv<T, VEC>(dst + row * ldd + c, a);
+    loadv<T, VEC>(src + row * lds + c, b);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) a[k] += b[k];
+    storev<T, VEC>(dst + row * ldd + c, a);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void copy_kernel(T* __restrict__ dst, long long ldd, const T* __restrict__ src, long long lds, int C,
+                            long long total) {
+  const int cpv = C / VEC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpv) * VEC;
+    const long long row = i / cpv;
+    float a[VEC];
+    loadv<T, VEC>(src + row * lds + c, a);
+    storev<T, VEC>(dst + row * ldd + c, a);
+  }
+}
+
+// fp32 rows [rows, C] (ld) -> T rows (ld)   (token features into a channel slice of the conv input)
+template <typename T>
+__global__ void cast_rows_kernel(const float* __restrict__ src, long long lds, T* __restrict__ dst, long long ldd, int C,
+                                 long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long row = i / C;
+    dst[row * ldd + c] = from_f<T>(src[row * lds + c]);
+  }
+}
+template <typename T>
+__global__ void uncast_rows_kernel(const T* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd, int C,
+                                   long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long row = i / C;
+    dst[row * ldd + c] = to_f(src[row * lds + c]);
+  }
+}
+
+// 2x2x2 max pool, first maximum in (kd,kh,kw) scan order wins (torch semantics: strict '>' update)
+template <typename T, int VEC>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo, int Do,
+                                   int Ho, int Wo, int C, long long total) {
+  const int cpv = C / VEC;
+  const int Hi = 2 * Ho, Wi = 2 * Wo, Di = 2 * Do;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpv) * VEC;
+    long long r = i / cpv;
+    const int w = r % Wo; r /= Wo;
+    const int h = r % Ho; r /= Ho;
+    const int d = r % Do;
+    const long long n = r / Do;
+    float m[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const long long row = ((n * Di + 2 * d + (t >> 2)) * Hi + 2 * h + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1);
+      float v[VEC];
+      loadv<T, VEC>(x + row * ldx + c, v);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) m[k] = (v[k] > m[k] || v[k] != v[k]) ? v[k] : m[k];
+    }
+    storev<T, VEC>(out + (i / cpv) * ldo + c, m);
+  }
+}
+
+// dx[argmax] (+)= dpool ; other 7 positions get 0 when !accumulate
+template <typename T, int VEC>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ dp, long long ldp,
+                                   T* __restrict__ dx, long long lddx, int Do, int Ho, int Wo, int C, int accumulate,
+                                   long long total) {
+  const int cpv = C / VEC;
+  const int Hi = 2 * Ho, Wi = 2 * Wo, Di = 2 * Do;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpv) * VEC;
+    long long r = i / cpv;
+    const int w = r % Wo; r /= Wo;
+    const int h = r % Ho; r /= Ho;
+    const int d = r % Do;
+    const long long n = r / Do;
+    float m[VEC], g[VEC];
+    int am[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { m[k] = -INFINITY; am[k] = 0; }
+    long long rows[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      rows[t] = ((n * Di + 2 * d + (t >> 2)) * Hi + 2 * h + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1);
+      float v[VEC];
+      loadv<T, VEC>(x + rows[t] * ldx + c, v);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if (v[k] > m[k] || v[k] != v[k]) { m[k] = v[k]; am[k] = t; }
+    }
+    loadv<T, VEC>(dp + (i / cpv) * ldp + c, g);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float o[VEC];
+      if (accumulate) loadv<T, VEC>(dx + rows[t] * lddx + c, o);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o[k] = (accumulate ? o[k] : 0.f) + (am[k] == t ? g[k] : 0.f);
+      storev<T, VEC>(dx + rows[t] * lddx + c, o);
+    }
+  }
+}
+
+// trilinear x2, align_corners=False: src = (dst+0.5)/2-0.5 clamped at 0
+__device__ __forceinline__ void up2_src(int o, int In, int& i0, int& i1, float& w1) {
+  float s = (o + 0.5f) * 0.5f - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  i1 = i0 + (i0 < In - 1 ? 1 : 0);
+  w1 = s - (float)i0;
+}
+
+template <typename T, int VEC>
+__global__ void upsample2_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo, int Di,
+                                     int Hi, int Wi, int C, long long total) {
+  const int cpv = C / VEC;
+  const int Do = 2 * Di, Ho = 2 * Hi, Wo = 2 * Wi;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpv) * VEC;
+    long long r = i / cpv;
+    const int w = r % Wo; r /= Wo;
+    const int h = r % Ho; r /= Ho;
+    const int d = r % Do;
+    const long long n = r / Do;
+    int d0, d1, h0, h1, w0, w1;
+    float fd, fh, fw;
+    up2_src(d, Di, d0, d1, fd);
+    up2_src(h, Hi, h0, h1, fh);
+    up2_src(w, Wi, w0, w1, fw);
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int dd = (t & 4) ? d1 : d0, hh = (t & 2) ? h1 : h0, ww = (t & 1) ? w1 : w0;
+      const float wt = ((t & 4) ? fd : 1.f - fd) * ((t & 2) ? fh : 1.f - fh) * ((t & 1) ? fw : 1.f - fw);
+      float v[VEC];
+      loadv<T, VEC>(x + (((n * Di + dd) * Hi + hh) * Wi + ww) * ldx + c, v);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+    }
+    storev<T, VEC>(out + (i / cpv) * ldo + c, acc);
+  }
+}
+
+// gather form of the transpose: input voxel i receives from outputs 2i-1 (.25), 2i (.75 | 1 at i=0),
+// 2i+1 (.75 | 1 at i=In-1), 2i+2 (.25)
+__device__ __forceinline__ void up2_bwd_taps(int i, int In, int* o, float* w) {
+  o[0] = 2 * i - 1; w[0] = (i >= 1) ? 0.25f : 0.f;
+  o[1] = 2 * i;     w[1] = (i == 0) ? 1.0f : 0.75f;
+  o[2] = 2 * i + 1; w[2] = (i == In - 1) ? 1.0f : 0.75f;
+  o[3] = 2 * i + 2; w[3] = (i <= In - 2) ? 0.25f : 0.f;
+}
+
+template <typename T, int VEC>
+__global__ void upsample2_bwd_kernel(const T* __restrict__ dout, long long ldd, T* __restrict__ dx, long long lddx, int Di,
+                                     int Hi, int Wi, int C, int accumulate, long long total) {
+  const int cpv = C / VEC;
+  const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpv) * VEC;
+    long long r = i / cpv;
+    const int w = r % Wi; r /= Wi;
+    const int h = r % Hi; r /= Hi;
+    const int d = r % Di;
+    const long long n = r / Di;
+    int od[4], oh[4], ow[4];
+    float wd[4], wh[4], ww[4];
+    up2_bwd_taps(d, Di, od, wd);
+    up2_bwd_taps(h, Hi, oh, wh);
+    up2_bwd_taps(w, Wi, ow, ww);
+    float acc[VEC];
+    if (accumulate) loadv<T, VEC>(dx + (i / cpv) * lddx + c, acc);
+    else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    }
+    for (int a = 0; a < 4; ++a) {
+      if (wd[a] == 0.f) continue;
+      for (int b = 0; b < 4; ++b) {
+        if (wh[b] == 0.f) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (ww[e] == 0.f) continue;
+          const float wt = wd[a] * wh[b] * ww[e];
+          float v[VEC];
+          loadv<T, VEC>(dout + (((n * Do + od[a]) * Ho + oh[b]) * Wo + ow[e]) * ldd + c, v);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+        }
+      }
+    }
+    storev<T, VEC>(dx + (i / cpv) * lddx + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 1x1x1 heads: out[n, k, v] (NCDHW, T) = sum_c a[n, v, c] * w[k, c] + b[k]
+// ---------------------------------------------------------------------------
+constexpr int MAXCLS = 8;
+
+template <typename T, int VEC>
+__global__ void head_fwd_kernel(const T* __restrict__ a, long long lda, const float* __restrict__ w,
+                                const float* __restrict__ b, T* __restrict__ out, long long V, int C, int ncls,
+                                long long total) {
+  extern __shared__ float sw[];  // [ncls][C] + [ncls]
+  for (int i = threadIdx.x; i < ncls * C; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < ncls; i += blockDim.x) sw[ncls * C + i] = b ? b[i] : 0.f;
+  __syncthreads();
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < total; row += (long long)gridDim.x * blockDim.x) {
+    float acc[MAXCLS];
+#pragma unroll
+    for (int k = 0; k < MAXCLS; ++k) acc[k] = (k < ncls) ? sw[ncls * C + k] : 0.f;
+    for (int c = 0; c < C; c += VEC) {
+      float x[VEC];
+      loadv<T, VEC>(a + row * lda + c, x);
+#pragma unroll
+      for (int k = 0; k < MAXCLS; ++k) {
+        if (k < ncls) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[k] = fmaf(x[j], sw[k * C + c + j], acc[k]);
+        }
+      }
+    }
+    const long long n = row / V, v = row % V;
+#pragma unroll
+    for (int k = 0; k < MAXCLS; ++k)
+      if (k < ncls) out[(n * ncls + k) * V + v] = from_f<T>(acc[k]);
+  }
+}
+
+// da[n, v, c] (+)= sum_k g[n, k, v] * w[k, c]
+template <typename T, int VEC>
+__global__ void head_dgrad_kernel(const T* __restrict__ g, const float* __restrict__ w, T* __restrict__ da, long long ldd,
+                                  long long V, int C, int ncls, int accumulate, long long total) {
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < ncls * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < total; row += (long long)gridDim.x * blockDim.x) {
+    const long long n = row / V, v = row % V;
+    float gk[MAXCLS];
+#pragma unroll
+    for (int k = 0; k < MAXCLS; ++k) gk[k] = (k < ncls) ? to_f(g[(n * ncls + k) * V + v]) : 0.f;
+    for (int c = 0; c < C; c += VEC) {
+      float o[VEC];
+      if (accumulate) loadv<T, VEC>(da + row * ldd + c, o);
+      else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < MAXCLS; ++k) {
+        if (k < ncls) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) o[j] = fmaf(gk[k], sw[k * C + c + j], o[j]);
+        }
+      }
+      storev<T, VEC>(da + row * ldd + c, o);
+    }
+  }
+}
+
+// partial[chunk][k][C+1]: dW[k][c] = sum_v g[k][v] a[v][c];  column C holds db[k]
+template <typename T>
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ a, long long lda,
+                                                        long long V, int C, int ncls, long long total, int rows_per_chunk,
+                                                        float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [lanes][ncls][C]
+  const int tid = threadIdx.x;
+  const int cb = min(C, 256);
+  const int lanes = 256 / cb;
+  const int lane = tid / cb;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(total, r0 + rows_per_chunk);
+  for (int cbase = 0; cbase < C; cbase += cb) {
+    const int c = cbase + tid % cb;
+    float acc[MAXCLS], accb[MAXCLS];
+#pragma unroll
+    for (int k = 0; k < MAXCLS; ++k) acc[k] = accb[k] = 0.f;
+    if (lane < lanes && c < C) {
+      for (long long row = r0 + lane; row < r1; row += lanes) {
+        const long long n = row / V, v = row % V;
+        const float x = to_f(a[row * lda + c]);
+#pragma unroll
+        for (int k = 0; k < MAXCLS; ++k) {
+          if (k < ncls) {
+            const float gv = to_f(g[(n * ncls + k) * V + v]);
+            acc[k] = fmaf(gv, x, acc[k]);
+            accb[k] += gv;
+          }
+        }
+      }
+    }
+    if (lane < lanes && c < C)
+      for (int k = 0; k < ncls; ++k) sm[(lane * ncls + k) * cb + (c - cbase)] = acc[k];
+    __syncthreads();
+    for (int i = tid; i < ncls * cb; i += 256) {
+      const int k = i / cb, cc = i % cb;
+      if (cbase + cc < C) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += sm[(l * ncls + k) * cb + cc];
+        partial[((long long)blockIdx.x * ncls + k) * (C + 1) + cbase + cc] = s;
+      }
+    }
+    __syncthreads();
+    if (cbase == 0) {  // bias: lanes of channel 0 hold complete sums over their rows
+      if (lane < lanes && tid % cb == 0)
+        for (int k = 0; k < ncls; ++k) sm[lane * ncls + k] = accb[k];
+      __syncthreads();
+      if (tid < ncls) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += sm[l * ncls + tid];
+        partial[((long long)blockIdx.x * ncls + tid) * (C + 1) + C] = s;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void head_wgrad_finalize_kernel(const float* __restrict__ partial, int chunks, int C, int ncls,
+                                           float* __restrict__ dw, float* __restrict__ db, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncls * (C + 1)) return;
+  const int k = i / (C + 1), c = i % (C + 1);
+  float s = 0.f;
+  for (int z = 0; z < chunks; ++z) s += partial[((long long)z * ncls + k) * (C + 1) + c];
+  if (c < C) dw[k * C + c] = accumulate ? dw[k * C + c] + s : s;
+  else if (db) db[k] = accumulate ? db[k] + s : s;
+}
+
+// x NCDHW fp32 [N, C, V] -> channels-last T [N, V, C] (ld)
+template <typename T>
+__global__ void ncdhw_to_cl_kernel(const float* __restrict__ x, T* __restrict__ out, long long ldo, long long V, int C,
+                                   long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / V, v = i % V;
+    for (int c = 0; c < C; ++c) out[i * ldo + c] = from_f<T>(x[(n * C + c) * V + v]);
+  }
+}
+
+int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+#define HDF_VEC_DISPATCH(vec_ok, ...) \
+  if (vec_ok) { constexpr int VEC = VecOf<T>::value; __VA_ARGS__; } else { constexpr int VEC = 1; __VA_ARGS__; }
+
+extern "C" {
+
+size_t hdf_reduce_workspace(int N, long long V, int C) {
+  return (size_t)N * reduce_chunks(V, N) * 2 * C * sizeof(double) + 256;
+}
+
+int hdf_instnorm_stats(int dtype, const void* y, long long ldy, int N, long long V, int C, float eps, float* mean,
+                       float* rstd, void* workspace, size_t ws_bytes, void* stream) {
+  HDF_REQUIRE(y && mean && rstd && workspace && ws_bytes >= hdf_reduce_workspace(N, V, C), "hdf_instnorm_stats: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  int chunks = 0;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    StatsF<T> f{(const T*)y, ldy, V};
+    int rc = launch_rowreduce<T>(f, y, ldy, nullptr, 0, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_stats");
+    if (rc) return rc;
+  });
+  stats_finalize_kernel<<<cdiv(N * C, 128), 128, 0, s>>>((const double*)workspace, chunks, C, V, eps, mean, rstd, N * C);
+  HDF_LAUNCH_CHECK("hdf_instnorm_stats/finalize");
+  return HDF_OK;
+}
+
+int hdf_instnorm_apply(int dtype, const void* y, long long ldy, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, const void* residual, long long ldr, void* out, long long ldo, int N,
+                       long long V, int C, int relu, void* stream) {
+  HDF_REQUIRE(y && mean && rstd && out, "hdf_instnorm_apply: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(y, ldy, C) && can_vec<T>(out, ldo, C) && (!residual || can_vec<T>(residual, ldr, C));
+    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * V * (C / VEC);
+        in_apply_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)y, ldy, mean, rstd, gamma, beta, (const T*)residual, ldr, (T*)out, ldo, V, C, relu, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_instnorm_apply");
+  return HDF_OK;
+}
+
+// dy = IN/ReLU backward; also (d)gamma/(d)beta.  s1/s2: [N*C] scratch outputs.
+int hdf_instnorm_bwd(int dtype, const void* dout, long long ldd, const void* y, long long ldy, const float* mean,
+                     const float* rstd, const float* gamma, const float* beta, void* dy, long long ldo, int N, long long V,
+                     int C, int relu, float* s1, float* s2, float* dgamma, float* dbeta, int accumulate_params,
+                     void* workspace, size_t ws_bytes, void* stream) {
+  HDF_REQUIRE(dout && y && mean && rstd && dy && s1 && s2 && workspace && ws_bytes >= hdf_reduce_workspace(N, V, C),
+              "hdf_instnorm_bwd: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  int chunks = 0;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    InBwdF<T> f{(const T*)dout, ldd, (const T*)y, ldy, V, mean, rstd, gamma, beta, C, relu};
+    int rc = launch_rowreduce<T>(f, dout, ldd, y, ldy, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_bwd/reduce");
+    if (rc) return rc;
+  });
+  sums_finalize_kernel<<<cdiv(N * C, 128), 128, 0, s>>>((const double*)workspace, chunks, C, s1, s2, N * C);
+  HDF_LAUNCH_CHECK("hdf_instnorm_bwd/finalize");
+  if (dgamma || dbeta) {
+    in_param_grads_kernel<<<cdiv(C, 128), 128, 0, s>>>(s1, s2, N, C, dgamma, dbeta, accumulate_params);
+    HDF_LAUNCH_CHECK("hdf_instnorm_bwd/params");
+  }
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(dout, ldd, C) && can_vec<T>(y, ldy, C) && can_vec<T>(dy, ldo, C);
+    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * V * (C / VEC);
+        in_bwd_apply_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)dout, ldd, (const T*)y, ldy, mean, rstd, gamma, beta, s1, s2, (T*)dy, ldo, V, C, relu, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_instnorm_bwd/apply");
+  return HDF_OK;
+}
+
+// out[C] (+)= sum over rows of x[rows, C]
+int hdf_colsum(int dtype, const void* x, long long ld, long long rows, int C, float* out, int accumulate, void* workspace,
+               size_t ws_bytes, void* stream) {
+  HDF_REQUIRE(x && out && workspace && ws_bytes >= hdf_reduce_workspace(1, rows, C), "hdf_colsum: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  int chunks = 0;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    ColSumF<T> f{(const T*)x, ld, rows};
+    int rc = launch_rowreduce<T>(f, x, ld, nullptr, 0, 1, rows, C, (double*)workspace, chunks, s, "hdf_colsum");
+    if (rc) return rc;
+  });
+  colsum_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>((const double*)workspace, chunks, C, out, accumulate);
+  HDF_LAUNCH_CHECK("hdf_colsum/finalize");
+  return HDF_OK;
+}
+
+int hdf_add_(int dtype, void* dst, long long ldd, const void* src, long long lds, long long rows, int C, void* stream) {
+  HDF_REQUIRE(dst && src, "hdf_add_: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(dst, ldd, C) && can_vec<T>(src, lds, C);
+    HDF_VEC_DISPATCH(vec, { long long total = rows * (C / VEC); add_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((T*)dst, ldd, (const T*)src, lds, C, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_add_");
+  return HDF_OK;
+}
+
+int hdf_copy_rows(int dtype, void* dst, long long ldd, const void* src, long long lds, long long rows, int C, void* stream) {
+  HDF_REQUIRE(dst && src, "hdf_copy_rows: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(dst, ldd, C) && can_vec<T>(src, lds, C);
+    HDF_VEC_DISPATCH(vec, { long long total = rows * (C / VEC); copy_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((T*)dst, ldd, (const T*)src, lds, C, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_copy_rows");
+  return HDF_OK;
+}
+
+int hdf_cast_rows_from_f32(int dtype, const float* src, long long lds, void* dst, long long ldd, long long rows, int C,
+                           void* stream) {
+  HDF_REQUIRE(dst && src, "hdf_cast_rows_from_f32: null pointer");
+  const long long total = rows * C;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    cast_rows_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(src, lds, (T*)dst, ldd, C, total);
+  });
+  HDF_LAUNCH_CHECK("hdf_cast_rows_from_f32");
+  return HDF_OK;
+}
+
+int hdf_cast_rows_to_f32(int dtype, const void* src, long long lds, float* dst, long long ldd, long long rows, int C,
+                         void* stream) {
+  HDF_REQUIRE(dst && src, "hdf_cast_rows_to_f32: null pointer");
+  const long long total = rows * C;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    uncast_rows_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)src, lds, dst, ldd, C, total);
+  });
+  HDF_LAUNCH_CHECK("hdf_cast_rows_to_f32");
+  return HDF_OK;
+}
+
+int hdf_maxpool2_fwd(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Do, int Ho, int Wo,
+                     int C, void* stream) {
+  HDF_REQUIRE(x && out, "hdf_maxpool2_fwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(out, ldo, C);
+    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * Do * Ho * Wo * (C / VEC); maxpool_fwd_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)x, ldx, (T*)out, ldo, Do, Ho, Wo, C, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_maxpool2_fwd");
+  return HDF_OK;
+}
+
+int hdf_maxpool2_bwd(int dtype, const void* x, long long ldx, const void* dpool, long long ldp, void* dx, long long lddx,
+                     int N, int Do, int Ho, int Wo, int C, int accumulate, void* stream) {
+  HDF_REQUIRE(x && dpool && dx, "hdf_maxpool2_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(dpool, ldp, C) && can_vec<T>(dx, lddx, C);
+    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * Do * Ho * Wo * (C / VEC); maxpool_bwd_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)x, ldx, (const T*)dpool, ldp, (T*)dx, lddx, Do, Ho, Wo, C, accumulate, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_maxpool2_bwd");
+  return HDF_OK;
+}
+
+int hdf_upsample2_fwd(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Di, int Hi, int Wi,
+                      int C, void* stream) {
+  HDF_REQUIRE(x && out, "hdf_upsample2_fwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(out, ldo, C);
+    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * Di * Hi * Wi * 8 * (C / VEC); upsample2_fwd_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)x, ldx, (T*)out, ldo, Di, Hi, Wi, C, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_upsample2_fwd");
+  return HDF_OK;
+}
+
+int hdf_upsample2_bwd(int dtype, const void* dout, long long ldd, void* dx, long long lddx, int N, int Di, int Hi, int Wi,
+                      int C, int accumulate, void* stream) {
+  HDF_REQUIRE(dout && dx, "hdf_upsample2_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(dout, ldd, C) && can_vec<T>(dx, lddx, C);
+    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * Di * Hi * Wi * (C / VEC); upsample2_bwd_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)dout, ldd, (T*)dx, lddx, Di, Hi, Wi, C, accumulate, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_upsample2_bwd");
+  return HDF_OK;
+}
+
+int hdf_head_fwd(int dtype, const void* a, long long lda, const float* w, const float* b, void* out, int N, long long V,
+                 int C, int ncls, void* stream) {
+  HDF_REQUIRE(a && w && out && ncls >= 1 && ncls <= MAXCLS, "hdf_head_fwd: bad args (n_cls must be 1..%d)", MAXCLS);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)N * V;
+  const size_t smem = (size_t)(ncls * C + ncls) * sizeof(float);
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const bool vec = can_vec<T>(a, lda, C);
+    HDF_VEC_DISPATCH(vec, { head_fwd_kernel<T, VEC><<<grid_for(total, 128), 128, smem, s>>>((const T*)a, lda, w, b, (T*)out, V, C, ncls, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_head_fwd");
+  return HDF_OK;
+}
+
+size_t hdf_head_bwd_workspace(int N, long long V, int C, int ncls) {
+  const long long total = (long long)N * V;
+  int chunks = (int)((total + 2047) / 2048);
+  if (chunks > 148 * 4) chunks = 148 * 4;
+  return (size_t)chunks * ncls * (C + 1) * sizeof(float);
+}
+
+// g: NCDHW [N, ncls, V] (T).  da (+)= g . w ; dw/db (+)= reductions
+int hdf_head_bwd(int dtype, const void* g, const void* a, long long lda, const float* w, void* da, long long ldd,
+                 float* dw, float* db, int N, long long V, int C, int ncls, int accumulate_da, int accumulate_params,
+                 void* workspace, size_t ws_bytes, void* stream) {
+  HDF_REQUIRE(g && a && w && da && dw && workspace && ncls >= 1 && ncls <= MAXCLS, "hdf_head_bwd: bad args");
+  HDF_REQUIRE(ws_bytes >= hdf_head_bwd_workspace(N, V, C, ncls), "hdf_head_bwd: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)N * V;
+  int chunks = (int)((total + 2047) / 2048);
+  if (chunks > 148 * 4) chunks = 148 * 4;
+  const int rpc = cdiv(total, chunks);
+  chunks = cdiv(total, rpc);
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    const int cb = C < 256 ? C : 256;
+    const size_t smem = (size_t)(256 / cb) * ncls * cb * sizeof(float) + 64;
+    head_wgrad_kernel<T><<<chunks, 256, smem, s>>>((const T*)g, (const T*)a, lda, V, C, ncls, total, rpc, (float*)workspace);
+    HDF_LAUNCH_CHECK("hdf_head_bwd/wgrad");
+    head_wgrad_finalize_kernel<<<cdiv(ncls * (C + 1), 128), 128, 0, s>>>((const float*)workspace, chunks, C, ncls, dw, db, accumulate_params);
+    HDF_LAUNCH_CHECK("hdf_head_bwd/finalize");
+    const bool vec = can_vec<T>(da, ldd, C);
+    const size_t smem2 = (size_t)ncls * C * sizeof(float);
+    HDF_VEC_DISPATCH(vec, { head_dgrad_kernel<T, VEC><<<grid_for(total, 128), 128, smem2, s>>>((const T*)g, w, (T*)da, ldd, V, C, ncls, accumulate_da, total); });
+  });
+  HDF_LAUNCH_CHECK("hdf_head_bwd/dgrad");
+  return HDF_OK;
+}
+
+int hdf_ncdhw_to_cl(int dtype, const float* x, void* out, long long ldo, int N, int C, long long V, void* stream) {
+  HDF_REQUIRE(x && out, "hdf_ncdhw_to_cl: null pointer");
+  const long long total = (long long)N * V;
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    ncdhw_to_cl_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, (T*)out, ldo, V, C, total);
+  });
+  HDF_LAUNCH_CHECK("hdf_ncdhw_to_cl");
+  return HDF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,478 @@
+"""Forward / backward executor of the H-DenseFormer 3D graph on libhdf_b200 kernels.
+
+The graph is the reference's (models/HDenseFormer.py:229-255); execution is not: activations are
+channels-last (NDHWC) in the compute dtype, every torch.cat is a channel slice of a pre-allocated
+buffer that producers write in place, the backward pass is hand-scheduled (no autograd tape per op),
+parameter gradients land in one flat fp32 arena (bucketed all-reduce friendly), dropout masks are
+recomputed from a counter-based RNG instead of being stored.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+GROWTH = 32      # models/HDenseFormer.py:79  growth_rate
+HEADS = 8        # models/HDenseFormer.py:79
+DROP_P = 0.5     # models/HDenseFormer.py:79,105
+
+
+class GradArena:
+    """Flat fp32 gradient buffer with one view per parameter, laid out in the order gradients become
+    final during backward (decoder first, transformer last) so that contiguous buckets can be
+    all-reduced while the rest of backward is still running."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], order: List[str]):
+        self.order = order
+        self.offsets = {}
+        off = 0
+        for k in order:
+            self.offsets[k] = off
+            off += (params[k].numel() + 31) // 32 * 32   # 128-byte aligned slices
+        self.total = off
+        dev = params[order[0]].device
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.views = {k: self.flat[self.offsets[k]: self.offsets[k] + params[k].numel()].view(params[k].shape) for k in order}
+
+    def zero_(self):
+        self.flat.zero_()
+
+
+class Config:
+    def __init__(self, in_channels, n_cls, n_filters, image_size, transformer_depth):
+        self.M = in_channels
+        self.n_cls = n_cls
+        self.nf = n_filters
+        self.image_size = tuple(image_size)
+        self.nblocks = transformer_depth // 4
+        self.E = 4 * n_filters
+        self.tok_grid = tuple(s // 16 for s in image_size)
+        self.ntok = self.tok_grid[0] * self.tok_grid[1] * self.tok_grid[2]
+
+
+def backward_param_order(cfg: Config, keys: List[str]) -> List[str]:
+    """Order in which parameter gradients are completed by Engine.backward."""
+    def grp(prefix):
+        return [k for k in keys if k.startswith(prefix)]
+    order: List[str] = []
+    for name in ["conv1x1.", "block_1_2_right.", "block_1_1_right.", "upconv_1.", "conv1x1_d1.", "block_2_2_right.",
+                 "block_2_1_right.", "upconv_2.", "conv1x1_d2.", "block_3_2_right.", "block_3_1_right.", "upconv_3.",
+                 "conv1x1_d3.", "block_4_2_left.", "block_4_1_left.", "block_3_2_left.", "block_3_1_left.",
+                 "block_2_2_left.", "block_2_1_left.", "block_1_2_left.", "block_1_1_left.", "up3.", "up2.", "up1.",
+                 "deep_conv."]:
+        order += grp(name)
+    for i in reversed(range(cfg.M)):
+        order += grp(f"attns.{i}.")
+    assert sorted(order) == sorted(keys), "parameter order table does not cover the state_dict"
+    return order
+
+
+class Ctx:
+    """Saved tensors of one forward pass."""
+    pass
+
+
+class Engine:
+    def __init__(self, cfg: Config):
+        self.cfg = cfg
+        self.use_tc = True   # tcgen05 convolution path when available (bf16 only)
+
+    # ------------------------------------------------------------------ conv helpers
+    def _conv_fwd(self, x, w, bias, out, mode=0):
+        """x: [N,D,H,W,Cin] view; w: torch-layout weight; out: [N,Do,Ho,Wo,Cout] view."""
+        if mode == 0:    # Conv3d weight [Cout, Cin, 27]
+            Cout, Cin = w.shape[0], w.shape[1]
+            wp = ops.conv_pack(w, Cin, Cout, 27, Cin * 27, False)
+        else:            # ConvTranspose3d weight [Cin, Cout, 27]
+            Cin, Cout = w.shape[0], w.shape[1]
+            wp = ops.conv_pack(w, Cin, Cout, Cout * 27, 27, False)
+        return ops.conv3d_fwd(x, wp, bias, out, mode)
+
+    def _conv_dgrad(self, dy, w, out, mode=0):
+        """input gradient of _conv_fwd(mode): mode 0 -> conv with flipped taps, swapped channels;
+        mode 1 (transposed conv) -> strided conv (mode 2)."""
+        if mode == 0:
+            Cout, Cin = w.shape[0], w.shape[1]
+            wp = ops.conv_pack(w, Cout, Cin, Cin * 27, 27, True)      # packed[tap][co][ci] = w[co][ci][26-tap]
+            return ops.conv3d_fwd(dy, wp, None, out, 0)
+        Cin, Cout = w.shape[0], w.shape[1]
+        wp = ops.conv_pack(w, Cout, Cin, 27, Cout * 27, False)         # packed[tap][co][ci] = w[ci][co][tap]
+        return ops.conv3d_fwd(dy, wp, None, out, 2)
+
+    def _conv_wgrad(self, x, dy, dw, mode=0):
+        if mode == 0:    # dw [Cout, Cin, 27]
+            Cin = dw.shape[1]
+            ops.conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
+        else:            # dw [Cin, Cout, 27]
+            Cout = dw.shape[1]
+            ops.conv3d_wgrad(x, dy, dw, Cout * 27, 27, 1)
+
+    # ------------------------------------------------------------------ BasicConv3d / UpConv
+    def _cnr_fwd(self, c: Ctx, name, x, P, out=None, residual=None, affine=True, bias=False):
+        """conv k3 -> InstanceNorm(+affine) -> ReLU (+ residual).  Saves raw conv output + stats."""
+        wkey = f"{name}.conv.weight" if affine else f"{name}.double_conv.0.weight"
+        w = P[wkey]
+        Cout = w.shape[0]
+        y = torch.empty((*x.shape[:-1], Cout), dtype=x.dtype, device=x.device)
+        self._conv_fwd(x, w, P[f"{name}.double_conv.0.bias"] if bias else None, y)
+        mean, rstd = ops.instnorm_stats(y)
+        if out is None:
+            out = torch.empty_like(y)
+        g = P[f"{name}.norm.weight"] if affine else None
+        b = P[f"{name}.norm.bias"] if affine else None
+        ops.instnorm_apply(y, mean, rstd, g, b, out, residual=residual, relu=True)
+        setattr(c, name, (x, y, mean, rstd))
+        return out
+
+    def _cnr_bwd(self, c: Ctx, name, dout, P, G, affine=True, bias=False, need_dx=True):
+        x, y, mean, rstd = getattr(c, name)
+        wkey = f"{name}.conv.weight" if affine else f"{name}.double_conv.0.weight"
+        w = P[wkey]
+        g = P[f"{name}.norm.weight"] if affine else None
+        b = P[f"{name}.norm.bias"] if affine else None
+        dy = ops.instnorm_bwd(dout, y, mean, rstd, g, b, G[f"{name}.norm.weight"] if affine else None,
+                              G[f"{name}.norm.bias"] if affine else None, relu=True)
+        self._conv_wgrad(x, dy, G[wkey])
+        if bias:
+            ops.colsum(dy, G[f"{name}.double_conv.0.bias"])
+        dx = None
+        if need_dx:
+            dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+            self._conv_dgrad(dy, w, dx)
+        return dx
+
+    # ------------------------------------------------------------------ DCT block
+    def _dct_block_fwd(self, P, pre, F, Cin_tok, R, B, training, seed, ids, saved):
+        """F: [R, E+128] feature buffer whose first E columns hold the block input.  Returns o1 (the
+        hidden of out_layer); the caller runs the last Linear so it can write into the next buffer."""
+        E = self.cfg.E
+        p = DROP_P if training else 0.0
+        dev = F.device
+        f32 = torch.float32
+        layers = []
+        for l in range(4):
+            q = f"{pre}layers.{l}."
+            Cl = E + GROWTH * l
+            h0 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+            ops.gemm(F[:, :Cl], P[q + "0.weight"], True, h0, bias=P[q + "0.bias"])
+            n1, m1, r1 = ops.layernorm_fwd(h0, P[q + "1.norm.weight"], P[q + "1.norm.bias"])
+            qkv = torch.empty((R, 3 * GROWTH), dtype=f32, device=dev)
+            ops.gemm(n1, P[q + "1.fn.to_qkv.weight"], True, qkv)
+            o, lse = ops.attention_fwd(qkv, B, R // B, HEADS, (GROWTH // HEADS) ** -0.5)
+            h1 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+            ida = ids()
+            ops.gemm(o, P[q + "1.fn.to_out.0.weight"], True, h1, bias=P[q + "1.fn.to_out.0.bias"], residual=h0, p=p, seed=seed,
+                     call_id=ida)
+            n2, m2, r2 = ops.layernorm_fwd(h1, P[q + "2.norm.weight"], P[q + "2.norm.bias"])
+            z1 = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
+            f1 = torch.empty_like(z1)
+            idb = ids()
+            ops.gemm(n2, P[q + "2.fn.net.0.weight"], True, f1, bias=P[q + "2.fn.net.0.bias"], pre=z1, act=1, p=p, seed=seed,
+                     call_id=idb)
+            h2 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+            idc = ids()
+            ops.gemm(f1, P[q + "2.fn.net.3.weight"], True, h2, bias=P[q + "2.fn.net.3.bias"], residual=h1, p=p, seed=seed,
+                     call_id=idc)
+            n3, m3, r3 = ops.layernorm_fwd(h2, P[q + "2.norm.weight"], P[q + "2.norm.bias"])
+            z1b = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
+            g1 = torch.empty_like(z1b)
+            idd = ids()
+            ops.gemm(n3, P[q + "2.fn.net.0.weight"], True, g1, bias=P[q + "2.fn.net.0.bias"], pre=z1b, act=1, p=p, seed=seed,
+                     call_id=idd)
+            ide = ids()
+            ops.gemm(g1, P[q + "2.fn.net.3.weight"], True, F[:, Cl:Cl + GROWTH], bias=P[q + "2.fn.net.3.bias"], p=p, seed=seed,
+                     call_id=ide)
+            layers.append(dict(h0=h0, n1=n1, m1=m1, r1=r1, qkv=qkv, o=o, lse=lse, h1=h1, n2=n2, m2=m2, r2=r2, z1=z1, f1=f1,
+                               h2=h2, n3=n3, m3=m3, r3=r3, z1b=z1b, g1=g1, ids=(ida, idb, idc, idd, ide)))
+        zo = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
+        o1 = torch.empty_like(zo)
+        idf = ids()
+        ops.gemm(F, P[pre + "out_layer.net.0.weight"], True, o1, bias=P[pre + "out_layer.net.0.bias"], pre=zo, act=1, p=p,
+                 seed=seed, call_id=idf)
+        saved.update(F=F, layers=layers, zo=zo, o1=o1, idf=idf)
+        return o1
+
+    def _dct_block_bwd(self, P, G, pre, saved, d_o1, R, B, training, seed):
+        """d_o1: grad wrt out_layer hidden (after GELU+dropout).  Returns dX = grad wrt block input [R,E] view."""
+        E = self.cfg.E
+        p = DROP_P if training else 0.0
+        F = saved["F"]
+        dev = F.device
+        f32 = torch.float32
+        dzo = ops.act_dropout_bwd(d_o1, saved["zo"], 1, p, seed, saved["idf"])
+        ops.gemm_at_b(dzo, F, G[pre + "out_layer.net.0.weight"])
+        ops.colsum(dzo, G[pre + "out_layer.net.0.bias"], accumulate=True)
+        dF = torch.empty_like(F)
+        ops.gemm(dzo, P[pre + "out_layer.net.0.weight"], False, dF)
+        scale = (GROWTH // HEADS) ** -0.5
+        for l in reversed(range(4)):
+            q = f"{pre}layers.{l}."
+            s = saved["layers"][l]
+            ida, idb, idc, idd, ide = s["ids"]
+            Cl = E + GROWTH * l
+            W1, W2 = P[q + "2.fn.net.0.weight"], P[q + "2.fn.net.3.weight"]
+            # features.append(ff(LN(h2)))
+            dzz = ops.act_dropout_bwd(dF[:, Cl:Cl + GROWTH], None, 0, p, seed, ide)
+            ops.gemm_at_b(dzz, s["g1"], G[q + "2.fn.net.3.weight"])
+            ops.colsum(dzz, G[q + "2.fn.net.3.bias"], accumulate=True)
+            dg1 = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
+            ops.gemm(dzz, W2, False, dg1)
+            dz1b = ops.act_dropout_bwd(dg1, s["z1b"], 1, p, seed, idd)
+            ops.gemm_at_b(dz1b, s["n3"], G[q + "2.fn.net.0.weight"])
+            ops.colsum(dz1b, G[q + "2.fn.net.0.bias"], accumulate=True)
+            dn3 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+            ops.gemm(dz1b, W1, False, dn3)
+            dh = torch.empty((R, GROWTH), dtype=f32, device=dev)      # running grad of the residual stream
+            ops.layernorm_bwd(dn3, s["h2"], s["m3"], s["r3"], P[q + "2.norm.weight"], dh, False, G[q + "2.norm.weight"],
+                              G[q + "2.norm.bias"])
+            # h2 = drop(f1 W2^T + b2) + h1
+            dzz2 = ops.act_dropout_bwd(dh, None, 0, p, seed, idc)
+            ops.gemm_at_b(dzz2, s["f1"], G[q + "2.fn.net.3.weight"])
+            ops.colsum(dzz2, G[q + "2.fn.net.3.bias"], accumulate=True)
+            df1 = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
+            ops.gemm(dzz2, W2, False, df1)
+            dz1 = ops.act_dropout_bwd(df1, s["z1"], 1, p, seed, idb)
+            ops.gemm_at_b(dz1, s["n2"], G[q + "2.fn.net.0.weight"])
+            ops.colsum(dz1, G[q + "2.fn.net.0.bias"], accumulate=True)
+            dn2 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+            ops.gemm(dz1, W1, False, dn2)
+            ops.layernorm_bwd(dn2, s["h1"], s["m2"], s["r2"], P[q + "2.norm.weight"], dh, True, G[q + "2.norm.weight"],
+                              G[q + "2.norm.bias"])
+            # h1 = drop(o Wo^T + bo) + h0
+            dzo_ = ops.act_dropout_bwd(dh, None, 0, p, seed, ida)
+            ops.gemm_at_b(dzo_, s["o"], G[q + "1.fn.to_out.0.weight"])
+            ops.colsum(dzo_, G[q + "1.fn.to_out.0.bias"], accumulate=True)
+            do = torch.empty((R, GROWTH), dtype=f32, device=dev)
+            ops.gemm(dzo_, P[q + "1.fn.to_out.0.weight"], False, do)
+            dqkv = ops.attention_bwd(s["qkv"], s["o"], do, s["lse"], B, R // B, HEADS, scale)
+            ops.gemm_at_b(dqkv, s["n1"], G[q + "1.fn.to_qkv.weight"])
+            dn1 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+            ops.gemm(dqkv, P[q + "1.fn.to_qkv.weight"], False, dn1)
+            ops.layernorm_bwd(dn1, s["h0"], s["m1"], s["r1"], P[q + "1.norm.weight"], dh, True, G[q + "1.norm.weight"],
+                              G[q + "1.norm.bias"])
+            # h0 = F[:, :Cl] W_l^T + b_l
+            ops.gemm_at_b(dh, F[:, :Cl], G[q + "0.weight"])
+            ops.colsum(dh, G[q + "0.bias"], accumulate=True)
+            ops.gemm(dh, P[q + "0.weight"], False, dF[:, :Cl], accumulate=True)
+        return dF[:, :E]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, P: Dict[str, torch.Tensor], x: torch.Tensor, dtype: torch.dtype, training: bool, seed: int,
+                save: bool = True):
+        cfg = self.cfg
+        ops.ensure_init(x)
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        B, M, D, H, W = x.shape
+        assert M == cfg.M and (D, H, W) == cfg.image_size, \
+            f"input {tuple(x.shape)} does not match in_channels={cfg.M}, image_size={cfg.image_size}"
+        nf, E = cfg.nf, cfg.E
+        dev = x.device
+        c = Ctx()
+        c.x, c.dtype, c.training, c.seed, c.B = x, dtype, training, seed, B
+        counter = [0]
+
+        def ids():
+            counter[0] += 1
+            return counter[0]
+
+        def empty(shape, dt=dtype):
+            return torch.empty(shape, dtype=dt, device=dev)
+
+        # ---------------- transformer branches (fp32 tokens), one per modality
+        d16 = cfg.tok_grid
+        ntok = cfg.ntok
+        R = B * ntok
+        FW = E + 4 * GROWTH
+        attnall = empty((B, *d16, E * M))
+        c.tr = []
+        p = DROP_P if training else 0.0
+        for i in range(M):
+            pre = f"attns.{i}."
+            tr = dict(blocks=[])
+            F = empty((R, FW), torch.float32)
+            tr["pe_id"] = ids()
+            ops.patch_embed_fwd(x, i, P[pre + "patch_embeddings.weight"], P[pre + "patch_embeddings.bias"],
+                                P[pre + "position_embeddings"], F[:, :E], p, seed, tr["pe_id"])
+            tok = None
+            for b in range(cfg.nblocks):
+                bp = f"{pre}blocks.{b}.0."
+                saved = {}
+                o1 = self._dct_block_fwd(P, bp, F, E, R, B, training, seed, ids, saved)
+                saved["idg"] = ids()
+                if b + 1 < cfg.nblocks:
+                    Fn = empty((R, FW), torch.float32)
+                    dst = Fn[:, :E]
+                else:
+                    Fn = None
+                    tok = empty((R, E), torch.float32)
+                    dst = tok
+                ops.gemm(o1, P[bp + "out_layer.net.3.weight"], True, dst, bias=P[bp + "out_layer.net.3.bias"], p=p, seed=seed,
+                         call_id=saved["idg"])
+                tr["blocks"].append(saved)
+                F = Fn
+            if cfg.nblocks == 0:
+                tok = F[:, :E]
+            ops.cast_from_f32(tok, attnall.view(R, E * M)[:, i * E:(i + 1) * E])
+            c.tr.append(tr)
+        c.attnall = attnall
+
+        # ---------------- up-sampling path of the transformer features (UpConv x4)
+        def upconv(name, xin):
+            a = self._cnr_fwd(c, name, xin, P, affine=False, bias=True)
+            up = empty((B, 2 * a.shape[1], 2 * a.shape[2], 2 * a.shape[3], a.shape[4]))
+            return ops.upsample2_fwd(a, up)
+
+        attnout = upconv("deep_conv", attnall)
+        at1 = upconv("up1", attnout)
+        at2 = upconv("up2", at1)
+        at3 = upconv("up3", at2)
+
+        # ---------------- encoder; skip tensors are written straight into the decoder concat buffers
+        xcl = ops.ncdhw_to_cl(x, dtype)
+        c.xcl = xcl
+        cat1 = empty((B, D, H, W, 2 * nf))
+        cat2 = empty((B, D // 2, H // 2, W // 2, 4 * nf))
+        cat3 = empty((B, D // 4, H // 4, W // 4, 8 * nf))
+        c.cat1, c.cat2, c.cat3 = cat1, cat2, cat3
+        a = self._cnr_fwd(c, "block_1_1_left", xcl, P)
+        ds0 = self._cnr_fwd(c, "block_1_2_left", a, P, out=cat1[..., nf:], residual=at3)
+        p1 = ops.maxpool2_fwd(ds0, empty((B, D // 2, H // 2, W // 2, nf)))
+        a = self._cnr_fwd(c, "block_2_1_left", p1, P)
+        ds1 = self._cnr_fwd(c, "block_2_2_left", a, P, out=cat2[..., 2 * nf:], residual=at2)
+        p2 = ops.maxpool2_fwd(ds1, empty((B, D // 4, H // 4, W // 4, 2 * nf)))
+        a = self._cnr_fwd(c, "block_3_1_left", p2, P)
+        ds2 = self._cnr_fwd(c, "block_3_2_left", a, P, out=cat3[..., 4 * nf:], residual=at1)
+        p3 = ops.maxpool2_fwd(ds2, empty((B, D // 8, H // 8, W // 8, 4 * nf)))
+        a = self._cnr_fwd(c, "block_4_1_left", p3, P)
+        x4 = self._cnr_fwd(c, "block_4_2_left", a, P, residual=attnout)
+        c.x4 = x4
+
+        # ---------------- decoder with deep-supervision heads
+        out3 = ops.head_fwd(x4, P["conv1x1_d3.weight"], P["conv1x1_d3.bias"])
+        self._conv_fwd(x4, P["upconv_3.weight"], P["upconv_3.bias"], cat3[..., :4 * nf], mode=1)
+        a = self._cnr_fwd(c, "block_3_1_right", cat3, P)
+        a32 = self._cnr_fwd(c, "block_3_2_right", a, P)
+        out2 = ops.head_fwd(a32, P["conv1x1_d2.weight"], P["conv1x1_d2.bias"])
+        self._conv_fwd(a32, P["upconv_2.weight"], P["upconv_2.bias"], cat2[..., :2 * nf], mode=1)
+        a = self._cnr_fwd(c, "block_2_1_right", cat2, P)
+        a22 = self._cnr_fwd(c, "block_2_2_right", a, P)
+        out1 = ops.head_fwd(a22, P["conv1x1_d1.weight"], P["conv1x1_d1.bias"])
+        self._conv_fwd(a22, P["upconv_1.weight"], P["upconv_1.bias"], cat1[..., :nf], mode=1)
+        a = self._cnr_fwd(c, "block_1_1_right", cat1, P)
+        a12 = self._cnr_fwd(c, "block_1_2_right", a, P)
+        out0 = ops.head_fwd(a12, P["conv1x1.weight"], P["conv1x1.bias"])
+        c.a32, c.a22, c.a12 = a32, a22, a12
+        return [out0, out1, out2, out3], (c if save else None)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], c: Ctx, gouts: List[Optional[torch.Tensor]],
+                 on_grads_ready=None):
+        """Fills G (views of the GradArena) with parameter gradients.  `on_grads_ready(last_key)` is called
+        whenever all gradients up to and including `last_key` (arena order) are final."""
+        cfg = self.cfg
+        nf, E, B = cfg.nf, cfg.E, c.B
+        dt = c.dtype
+        dev = c.x.device
+        notify = on_grads_ready or (lambda k: None)
+
+        def empty(shape, dtype=dt):
+            return torch.empty(shape, dtype=dtype, device=dev)
+
+        def gout(i, like_shape):
+            g = gouts[i]
+            if g is None:
+                return torch.zeros(like_shape, dtype=dt, device=dev)
+            return g.to(dt).contiguous()
+
+        def head_bwd(name, g, a, da, accumulate_da):
+            ops.head_bwd(g, a, P[name + ".weight"].view(cfg.n_cls, -1), da, G[name + ".weight"], G[name + ".bias"], accumulate_da)
+
+        def convt_bwd(name, du, a_in):
+            """du: grad of the transposed-conv output (a channel-slice view); returns fresh grad wrt its input"""
+            da = empty(a_in.shape)
+            self._conv_dgrad(du, P[name + ".weight"], da, mode=1)
+            self._conv_wgrad(a_in, du, G[name + ".weight"], mode=1)
+            ops.colsum(du, G[name + ".bias"])
+            return da
+
+        D, H, W = cfg.image_size
+        # ---- level 0 (full resolution)
+        dA = empty(c.a12.shape)
+        head_bwd("conv1x1", gout(0, (B, cfg.n_cls, D, H, W)), c.a12, dA, False)
+        dA = self._cnr_bwd(c, "block_1_2_right", dA, P, G)
+        dcat1 = self._cnr_bwd(c, "block_1_1_right", dA, P, G)
+        dA = convt_bwd("upconv_1", dcat1[..., :nf], c.a22)
+        head_bwd("conv1x1_d1", gout(1, (B, cfg.n_cls, D // 2, H // 2, W // 2)), c.a22, dA, True)
+        notify("conv1x1_d1.bias")
+        # ---- level 1
+        dA = self._cnr_bwd(c, "block_2_2_right", dA, P, G)
+        dcat2 = self._cnr_bwd(c, "block_2_1_right", dA, P, G)
+        dA = convt_bwd("upconv_2", dcat2[..., :2 * nf], c.a32)
+        head_bwd("conv1x1_d2", gout(2, (B, cfg.n_cls, D // 4, H // 4, W // 4)), c.a32, dA, True)
+        notify("conv1x1_d2.bias")
+        # ---- level 2
+        dA = self._cnr_bwd(c, "block_3_2_right", dA, P, G)
+        dcat3 = self._cnr_bwd(c, "block_3_1_right", dA, P, G)
+        dx4 = convt_bwd("upconv_3", dcat3[..., :4 * nf], c.x4)
+        head_bwd("conv1x1_d3", gout(3, (B, cfg.n_cls, D // 8, H // 8, W // 8)), c.x4, dx4, True)
+        notify("conv1x1_d3.bias")
+        # ---- bottleneck + encoder (dx4 is also the gradient of attnout through the residual add)
+        dA = self._cnr_bwd(c, "block_4_2_left", dx4, P, G)
+        dp3 = self._cnr_bwd(c, "block_4_1_left", dA, P, G)
+        dds2 = dcat3[..., 4 * nf:]
+        ops.maxpool2_bwd(c.cat3[..., 4 * nf:], dp3, dds2, True)
+        dA = self._cnr_bwd(c, "block_3_2_left", dds2, P, G)
+        dp2 = self._cnr_bwd(c, "block_3_1_left", dA, P, G)
+        dds1 = dcat2[..., 2 * nf:]
+        ops.maxpool2_bwd(c.cat2[..., 2 * nf:], dp2, dds1, True)
+        notify("block_3_1_left.norm.bias")
+        dA = self._cnr_bwd(c, "block_2_2_left", dds1, P, G)
+        dp1 = self._cnr_bwd(c, "block_2_1_left", dA, P, G)
+        dds0 = dcat1[..., nf:]
+        ops.maxpool2_bwd(c.cat1[..., nf:], dp1, dds0, True)
+        dA = self._cnr_bwd(c, "block_1_2_left", dds0, P, G)
+        self._cnr_bwd(c, "block_1_1_left", dA, P, G, need_dx=False)
+        notify("block_1_1_left.norm.bias")
+
+        # ---- transformer-feature up path: at3 <- up3 <- at2 <- up2 <- at1 <- up1 <- attnout <- deep_conv <- attnall
+        def upconv_bwd(name, dup, extra):
+            """dup: grad wrt the upsampled output; extra: additional grad wrt this UpConv's *input* (or None)"""
+            xin, y, _, _ = getattr(c, name)
+            da = empty(y.shape)
+            ops.upsample2_bwd(dup, da, False)
+            dx = self._cnr_bwd(c, name, da, P, G, affine=False, bias=True)
+            if extra is not None:
+                ops.add_(dx, extra)
+            return dx
+
+        dat2 = upconv_bwd("up3", dds0, dds1)
+        dat1 = upconv_bwd("up2", dat2, dds2)
+        dattnout = upconv_bwd("up1", dat1, dx4)
+        dattnall = upconv_bwd("deep_conv", dattnout, None)
+        notify("deep_conv.double_conv.0.bias")
+
+        # ---- transformer branches
+        R = B * cfg.ntok
+        p = DROP_P if c.training else 0.0
+        for i in reversed(range(cfg.M)):
+            pre = f"attns.{i}."
+            tr = c.tr[i]
+            dtok = empty((R, E), torch.float32)
+            ops.cast_to_f32(dattnall.view(R, E * cfg.M)[:, i * E:(i + 1) * E], dtok)
+            for b in reversed(range(cfg.nblocks)):
+                bp = f"{pre}blocks.{b}.0."
+                saved = tr["blocks"][b]
+                dz = ops.act_dropout_bwd(dtok, None, 0, p, c.seed, saved["idg"])
+                ops.gemm_at_b(dz, saved["o1"], G[bp + "out_layer.net.3.weight"])
+                ops.colsum(dz, G[bp + "out_layer.net.3.bias"], accumulate=True)
+                d_o1 = empty((R, 2 * GROWTH), torch.float32)
+                ops.gemm(dz, P[bp + "out_layer.net.3.weight"], False, d_o1)
+                dtok = self._dct_block_bwd(P, G, bp, saved, d_o1, R, B, c.training, c.seed)
+            # patch embedding: tok = drop(conv(img) + bias + pos)
+            dpe = ops.act_dropout_bwd(dtok, None, 0, p, c.seed, tr["pe_id"])
+            ops.posemb_grad(dpe, G[pre + "position_embeddings"], B, cfg.ntok, E)
+            ops.colsum(dpe, G[pre + "patch_embeddings.bias"])
+            ops.patch_embed_wgrad(c.x, i, dpe, G[pre + "patch_embeddings.weight"])
+            notify([k for k in G if k.startswith(pre)][-1])

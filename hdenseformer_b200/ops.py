@@ -1,0 +1,322 @@
+"""Thin typed wrappers over the C ABI: torch tensors in, torch tensors out.  torch is used for
+device memory and streams only; every arithmetic op here is a kernel of libhdf_b200.so."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _C
+
+_DT = {torch.float32: _C.F32, torch.bfloat16: _C.BF16}
+
+
+def _lib():
+    return _C.load()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ld(t: torch.Tensor) -> int:
+    """channel stride (elements) of a channels-last view [..., C]"""
+    assert t.stride(-1) == 1, "innermost (channel) dim must be contiguous"
+    ld = t.stride(-2)
+    # all leading dims must be densely packed on top of ld
+    exp = ld
+    for i in range(t.dim() - 2, -1, -1):
+        assert t.shape[i] == 1 or t.stride(i) == exp, f"view is not row-dense: shape {tuple(t.shape)} stride {t.stride()}"
+        exp *= t.shape[i]
+    return ld
+
+
+class Workspace:
+    """One growable scratch buffer per (device, stream)."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, nbytes: int) -> torch.Tensor:
+        key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device="cuda")
+            cls._bufs[key] = buf
+        return buf
+
+
+def ensure_init(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _C.HDFError("hdenseformer_b200 has no CPU path: tensors must live on a CUDA (sm_100a) device")
+    _C.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+# ----------------------------------------------------------------------------- conv
+def conv_pack(w: torch.Tensor, A: int, B: int, stride_a: int, stride_b: int, flip: bool) -> torch.Tensor:
+    out = torch.empty((27, A, B), dtype=torch.float32, device=w.device)
+    _C.check(_lib().hdf_conv_pack_weights(_p(w), _p(out), A, B, stride_a, stride_b, int(flip), _s()), "conv_pack")
+    return out
+
+
+def conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, mode: int = 0):
+    N, Do, Ho, Wo, Cout = out.shape
+    Cin = x.shape[-1]
+    _C.check(_lib().hdf_conv3d_fwd(_DT[x.dtype], mode, _p(x), _ld(x), _p(wp), _p(bias), _p(out), _ld(out), N, Do, Ho, Wo, Cin,
+                                   Cout, _s()), "conv3d_fwd")
+    return out
+
+
+def conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, stride_ci: int, stride_co: int, mode: int = 0,
+                 accumulate: bool = False):
+    N, Do, Ho, Wo, Cout = dy.shape
+    Cin = x.shape[-1]
+    nb = _lib().hdf_conv3d_wgrad_workspace(N, Do, Ho, Wo, Cin, Cout)
+    ws = Workspace.get(nb)
+    _C.check(_lib().hdf_conv3d_wgrad(_DT[x.dtype], mode, _p(x), _ld(x), _p(dy), _ld(dy), _p(dw), stride_ci, stride_co, N, Do,
+                                     Ho, Wo, Cin, Cout, _p(ws), ws.numel(), int(accumulate), _s()), "conv3d_wgrad")
+
+
+# ----------------------------------------------------------------------------- instance norm & friends
+def instnorm_stats(y: torch.Tensor, eps: float = 1e-5):
+    N, C = y.shape[0], y.shape[-1]
+    V = y.numel() // (N * C)
+    mean = torch.empty((N, C), dtype=torch.float32, device=y.device)
+    rstd = torch.empty_like(mean)
+    ws = Workspace.get(_lib().hdf_reduce_workspace(N, V, C))
+    _C.check(_lib().hdf_instnorm_stats(_DT[y.dtype], _p(y), _ld(y), N, V, C, eps, _p(mean), _p(rstd), _p(ws), ws.numel(), _s()),
+             "instnorm_stats")
+    return mean, rstd
+
+
+def instnorm_apply(y, mean, rstd, gamma, beta, out, residual=None, relu=True):
+    N, C = y.shape[0], y.shape[-1]
+    V = y.numel() // (N * C)
+    _C.check(_lib().hdf_instnorm_apply(_DT[y.dtype], _p(y), _ld(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual),
+                                       _ld(residual) if residual is not None else 0, _p(out), _ld(out), N, V, C, int(relu),
+                                       _s()), "instnorm_apply")
+    return out
+
+
+def instnorm_bwd(dout, y, mean, rstd, gamma, beta, dgamma, dbeta, relu=True, accumulate_params=False):
+    N, C = y.shape[0], y.shape[-1]
+    V = y.numel() // (N * C)
+    dy = torch.empty(y.shape, dtype=y.dtype, device=y.device)
+    s1 = torch.empty((N, C), dtype=torch.float32, device=y.device)
+    s2 = torch.empty_like(s1)
+    ws = Workspace.get(_lib().hdf_reduce_workspace(N, V, C))
+    _C.check(_lib().hdf_instnorm_bwd(_DT[y.dtype], _p(dout), _ld(dout), _p(y), _ld(y), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                                     _p(dy), _ld(dy), N, V, C, int(relu), _p(s1), _p(s2), _p(dgamma), _p(dbeta),
+                                     int(accumulate_params), _p(ws), ws.numel(), _s()), "instnorm_bwd")
+    return dy
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, accumulate=False):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    ws = Workspace.get(_lib().hdf_reduce_workspace(1, rows, C))
+    _C.check(_lib().hdf_colsum(_DT[x.dtype], _p(x), _ld(x), rows, C, _p(out), int(accumulate), _p(ws), ws.numel(), _s()), "colsum")
+
+
+def add_(dst: torch.Tensor, src: torch.Tensor):
+    C = dst.shape[-1]
+    _C.check(_lib().hdf_add_(_DT[dst.dtype], _p(dst), _ld(dst), _p(src), _ld(src), dst.numel() // C, C, _s()), "add_")
+    return dst
+
+
+def copy_rows(dst: torch.Tensor, src: torch.Tensor):
+    C = dst.shape[-1]
+    _C.check(_lib().hdf_copy_rows(_DT[dst.dtype], _p(dst), _ld(dst), _p(src), _ld(src), dst.numel() // C, C, _s()), "copy_rows")
+    return dst
+
+
+def cast_from_f32(src: torch.Tensor, dst: torch.Tensor):
+    C = dst.shape[-1]
+    _C.check(_lib().hdf_cast_rows_from_f32(_DT[dst.dtype], _p(src), _ld(src), _p(dst), _ld(dst), dst.numel() // C, C, _s()),
+             "cast_from_f32")
+
+
+def cast_to_f32(src: torch.Tensor, dst: torch.Tensor):
+    C = dst.shape[-1]
+    _C.check(_lib().hdf_cast_rows_to_f32(_DT[src.dtype], _p(src), _ld(src), _p(dst), _ld(dst), dst.numel() // C, C, _s()),
+             "cast_to_f32")
+
+
+def maxpool2_fwd(x: torch.Tensor, out: torch.Tensor):
+    N, Do, Ho, Wo, C = out.shape
+    _C.check(_lib().hdf_maxpool2_fwd(_DT[x.dtype], _p(x), _ld(x), _p(out), _ld(out), N, Do, Ho, Wo, C, _s()), "maxpool2_fwd")
+    return out
+
+
+def maxpool2_bwd(x: torch.Tensor, dpool: torch.Tensor, dx: torch.Tensor, accumulate: bool):
+    N, Do, Ho, Wo, C = dpool.shape
+    _C.check(_lib().hdf_maxpool2_bwd(_DT[x.dtype], _p(x), _ld(x), _p(dpool), _ld(dpool), _p(dx), _ld(dx), N, Do, Ho, Wo, C,
+                                     int(accumulate), _s()), "maxpool2_bwd")
+    return dx
+
+
+def upsample2_fwd(x: torch.Tensor, out: torch.Tensor):
+    N, Di, Hi, Wi, C = x.shape
+    _C.check(_lib().hdf_upsample2_fwd(_DT[x.dtype], _p(x), _ld(x), _p(out), _ld(out), N, Di, Hi, Wi, C, _s()), "upsample2_fwd")
+    return out
+
+
+def upsample2_bwd(dout: torch.Tensor, dx: torch.Tensor, accumulate: bool = False):
+    N, Di, Hi, Wi, C = dx.shape
+    _C.check(_lib().hdf_upsample2_bwd(_DT[dx.dtype], _p(dout), _ld(dout), _p(dx), _ld(dx), N, Di, Hi, Wi, C, int(accumulate),
+                                      _s()), "upsample2_bwd")
+    return dx
+
+
+def ncdhw_to_cl(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    N, Cc = x.shape[0], x.shape[1]
+    out = torch.empty((N, *x.shape[2:], Cc), dtype=dtype, device=x.device)
+    V = x.numel() // (N * Cc)
+    _C.check(_lib().hdf_ncdhw_to_cl(_DT[dtype], _p(x), _p(out), Cc, N, Cc, V, _s()), "ncdhw_to_cl")
+    return out
+
+
+# ----------------------------------------------------------------------------- heads
+def head_fwd(a: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    N, C = a.shape[0], a.shape[-1]
+    V = a.numel() // (N * C)
+    ncls = w.shape[0]
+    out = torch.empty((N, ncls, *a.shape[1:4]), dtype=a.dtype, device=a.device)
+    _C.check(_lib().hdf_head_fwd(_DT[a.dtype], _p(a), _ld(a), _p(w), _p(b), _p(out), N, V, C, ncls, _s()), "head_fwd")
+    return out
+
+
+def head_bwd(g: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor, dw: torch.Tensor, db: torch.Tensor,
+             accumulate_da: bool, accumulate_params: bool = False):
+    N, C = a.shape[0], a.shape[-1]
+    V = a.numel() // (N * C)
+    ncls = w.shape[0]
+    assert g.is_contiguous() and g.dtype == a.dtype
+    ws = Workspace.get(_lib().hdf_head_bwd_workspace(N, V, C, ncls))
+    _C.check(_lib().hdf_head_bwd(_DT[a.dtype], _p(g), _p(a), _ld(a), _p(w), _p(da), _ld(da), _p(dw), _p(db), N, V, C, ncls,
+                                 int(accumulate_da), int(accumulate_params), _p(ws), ws.numel(), _s()), "head_bwd")
+
+
+# ----------------------------------------------------------------------------- tokens (fp32 rows)
+def gemm(A, Bm, b_is_nk, out, bias=None, residual=None, pre=None, act=0, p=0.0, seed=0, call_id=0, accumulate=False):
+    """out[M,N] = epi(A[M,K] @ (Bm^T if b_is_nk else Bm))"""
+    M, K = A.shape
+    N = out.shape[1]
+    _C.check(_lib().hdf_gemm_rowmajor(_p(A), A.stride(0), _p(Bm), Bm.stride(0), int(b_is_nk), _p(out), out.stride(0), M, N, K,
+                                      _p(bias), _p(residual), residual.stride(0) if residual is not None else 0, _p(pre),
+                                      act, float(p), seed, call_id, int(accumulate), _s()), "gemm")
+    return out
+
+
+def gemm_at_b(A, Bm, out, accumulate=True):
+    """out[M,N] (+)= A[K,M]^T @ Bm[K,N]   (out dense)"""
+    K, M = A.shape
+    N = Bm.shape[1]
+    assert out.is_contiguous() and out.numel() == M * N
+    ws = Workspace.get(_lib().hdf_gemm_at_b_workspace(M, N, K))
+    _C.check(_lib().hdf_gemm_at_b(_p(A), A.stride(0), _p(Bm), Bm.stride(0), _p(out), M, N, K, _p(ws), ws.numel(),
+                                  int(accumulate), _s()), "gemm_at_b")
+
+
+def act_dropout_bwd(dy, pre, act, p, seed, call_id):
+    M, N = dy.shape
+    dz = torch.empty((M, N), dtype=torch.float32, device=dy.device)
+    _C.check(_lib().hdf_act_dropout_bwd(_p(dy), dy.stride(0), _p(pre), _p(dz), N, M, N, act, float(p), seed, call_id, _s()),
+             "act_dropout_bwd")
+    return dz
+
+
+def add_rows_f32(dst, src, accumulate):
+    rows, Cc = src.shape
+    _C.check(_lib().hdf_add_rows_f32(_p(dst), dst.stride(0), _p(src), src.stride(0), rows, Cc, int(accumulate), _s()),
+             "add_rows_f32")
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    M, Cc = x.shape
+    out = torch.empty((M, Cc), dtype=torch.float32, device=x.device)
+    mean = torch.empty((M,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    _C.check(_lib().hdf_layernorm_fwd(_p(x), x.stride(0), _p(gamma), _p(beta), _p(out), Cc, _p(mean), _p(rstd), M, Cc, eps, _s()),
+             "layernorm_fwd")
+    return out, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta):
+    M, Cc = x.shape
+    ws = Workspace.get(_lib().hdf_layernorm_bwd_workspace(M, Cc))
+    _C.check(_lib().hdf_layernorm_bwd(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(mean), _p(rstd), _p(gamma), _p(dx),
+                                      dx.stride(0), int(accumulate_dx), _p(dgamma), _p(dbeta), 1, M, Cc, _p(ws), ws.numel(),
+                                      _s()), "layernorm_bwd")
+
+
+def attention_fwd(qkv, B, N, H, scale):
+    R, three = qkv.shape
+    inner = three // 3
+    o = torch.empty((R, inner), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+    _C.check(_lib().hdf_attention_fwd(_p(qkv), qkv.stride(0), _p(o), inner, _p(lse), B, N, H, scale, _s()), "attention_fwd")
+    return o, lse
+
+
+def attention_bwd(qkv, o, dout, lse, B, N, H, scale):
+    dqkv = torch.empty_like(qkv)
+    _C.check(_lib().hdf_attention_bwd(_p(qkv), qkv.stride(0), _p(o), o.stride(0), _p(dout), dout.stride(0), _p(lse), _p(dqkv),
+                                      dqkv.stride(0), B, N, H, scale, _s()), "attention_bwd")
+    return dqkv
+
+
+def patch_embed_fwd(img, modality, weight, bias, pos, out, p, seed, call_id):
+    B, Mch, D, H, W = img.shape
+    E = weight.shape[0]
+    _C.check(_lib().hdf_patch_embed_fwd(_p(img), B, Mch, modality, D, H, W, _p(weight), _p(bias), _p(pos), _p(out),
+                                        out.stride(0), E, float(p), seed, call_id, _s()), "patch_embed_fwd")
+
+
+def patch_embed_wgrad(img, modality, dtok, dweight, accumulate=False):
+    B, Mch, D, H, W = img.shape
+    E = dweight.shape[0]
+    ws = Workspace.get(_lib().hdf_patch_embed_wgrad_workspace(B, D, H, W, E))
+    _C.check(_lib().hdf_patch_embed_wgrad(_p(img), B, Mch, modality, D, H, W, _p(dtok), dtok.stride(0), _p(dweight), E, _p(ws),
+                                          ws.numel(), int(accumulate), _s()), "patch_embed_wgrad")
+
+
+def posemb_grad(dtok, dpos, B, ntok, E, accumulate=False):
+    _C.check(_lib().hdf_posemb_grad(_p(dtok), dtok.stride(0), _p(dpos), B, ntok, E, int(accumulate), _s()), "posemb_grad")
+
+
+# ----------------------------------------------------------------------------- loss / sliding window
+def loss_level_fwd(logits, target, cw, level, ignore_index, smooth, level_weight, ce_w, dice_w, sums, out_level, total):
+    B, Cc, Dl, Hl, Wl = logits.shape
+    has_ig = ignore_index is not None
+    _C.check(_lib().hdf_loss_level_fwd(_DT[logits.dtype], _p(logits), _p(target), _p(cw), B, Cc, Dl, Hl, Wl, 1 << level,
+                                       ignore_index if has_ig else -1, int(has_ig), smooth, level_weight, ce_w, dice_w,
+                                       _p(sums), _p(out_level), _p(total), _s()), "loss_level_fwd")
+
+
+def loss_level_bwd(logits, target, cw, level, ignore_index, smooth, level_weight, ce_w, dice_w, sums, grad_out, dlogits):
+    B, Cc, Dl, Hl, Wl = logits.shape
+    has_ig = ignore_index is not None
+    _C.check(_lib().hdf_loss_level_bwd(_DT[logits.dtype], _p(logits), _p(target), _p(cw), B, Cc, Dl, Hl, Wl, 1 << level,
+                                       ignore_index if has_ig else -1, int(has_ig), smooth, level_weight, ce_w, dice_w,
+                                       _p(sums), _p(grad_out), _p(dlogits), _s()), "loss_level_bwd")
+
+
+def sw_accumulate(logits, agg, x0, y0, z0):
+    _, Cc, px, py, pz = logits.shape
+    _, X, Y, Z = agg.shape
+    _C.check(_lib().hdf_sw_accumulate(_DT[logits.dtype], _p(logits), _p(agg), Cc, X, Y, Z, x0, y0, z0, px, py, pz, _s()),
+             "sw_accumulate")
+
+
+def sw_finalize(agg, steps, patch, normalise=True):
+    Cc, X, Y, Z = agg.shape
+    mask = torch.empty((X, Y, Z), dtype=torch.int64, device=agg.device)
+    arr = [(ctypes.c_int * len(s))(*s) for s in steps]
+    _C.check(_lib().hdf_sw_finalize(_p(agg), _p(mask), Cc, X, Y, Z, arr[0], len(steps[0]), arr[1], len(steps[1]), arr[2],
+                                    len(steps[2]), patch[0], patch[1], patch[2], int(normalise), _s()), "sw_finalize")
+    return mask

@@ -1,0 +1,197 @@
+"""Host-side drivers of the hot path, mirroring the reference's call sites.
+
+  train_step                 trainer.py:361-380   (H2D, autocast forward, loss outside autocast, zero_grad,
+                                                    backward, optimizer step; no per-step host sync)
+  GradBucketer / DataParallelTrainer
+                             trainer.py:228-229   (nn.DataParallel -> one process per GPU, NCCL all-reduce of the
+                                                    flat gradient arena, bucket by bucket while backward runs)
+  cal_steps                  trainer.py:595-618
+  inference_slidingwindow    trainer.py:488-593   (patches sharded across ranks; analytic count map)
+  compute_dice               trainer.py:919-945
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+# ----------------------------------------------------------------------------- sliding window (host logic)
+
+
+def cal_steps(image_size: Sequence[int], patch_size: Sequence[int], step_size: Sequence[int]) -> List[List[int]]:
+    """Window start offsets per axis (trainer.py:595-618)."""
+    steps = []
+    for dim in range(len(image_size)):
+        if image_size[dim] <= patch_size[dim]:
+            steps.append([0])
+            continue
+        max_step_value = image_size[dim] - patch_size[dim]
+        num_steps = int(np.ceil(max_step_value / step_size[dim])) + 1
+        actual = max_step_value / (num_steps - 1)
+        steps.append([int(np.round(actual * i)) for i in range(num_steps)])
+    return steps
+
+
+def enumerate_patches(steps: List[List[int]]) -> List[Tuple[int, int, int]]:
+    """Patch origins in the reference's loop order (x outermost, z innermost; trainer.py:530-541)."""
+    return [(x, y, z) for x in steps[0] for y in steps[1] for z in steps[2]]
+
+
+def shard_patches(patches: List[Tuple[int, int, int]], rank: int, world: int) -> List[Tuple[int, int, int]]:
+    """Round-robin patch ownership: rank r takes patches r, r+world, ...."""
+    return patches[rank::world]
+
+
+@torch.no_grad()
+def inference_slidingwindow(net, image, n_cls: int, patch_size: Sequence[int], step_size: Sequence[int],
+                            use_bf16: bool = False, group=None, return_prob: bool = False):
+    """Sliding-window inference of one volume `image` [M, X, Y, Z] (numpy or tensor, host or device).
+
+    Every rank of `group` (or the single process) evaluates its share of the patches and accumulates
+    softmax probabilities into a private fp32 buffer; the buffers are summed with one all-reduce, then
+    normalised by the analytic per-voxel window count and arg-maxed on device.  Returns the int64 mask
+    [X, Y, Z] on the device (and the averaged probabilities if return_prob)."""
+    from . import ops
+    dev = next(net.parameters()).device
+    if isinstance(image, np.ndarray):
+        image = torch.from_numpy(image)
+    image = image.float()
+    M, X, Y, Z = image.shape
+    for s, p in zip((X, Y, Z), patch_size):
+        if s < p:
+            raise ValueError(f"volume {(X, Y, Z)} smaller than patch {tuple(patch_size)}: position embeddings have a fixed "
+                             "token count (models/HDenseFormer.py:119)")
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    steps = cal_steps((X, Y, Z), patch_size, step_size)
+    mine = shard_patches(enumerate_patches(steps), rank, world)
+    was_training = net.training
+    net.eval()
+    agg = torch.zeros((n_cls, X, Y, Z), dtype=torch.float32, device=dev)
+    px, py, pz = patch_size
+    if image.device != dev and not image.is_pinned():
+        image = image.pin_memory() if torch.cuda.is_available() else image
+    for (x, y, z) in mine:
+        data = image[None, :, x:x + px, y:y + py, z:z + pz].to(dev, non_blocking=True).contiguous()
+        if use_bf16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = net(data)[0]
+        else:
+            logits = net(data)[0]
+        ops.sw_accumulate(logits.contiguous(), agg, x, y, z)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM, group=group)
+    mask = ops.sw_finalize(agg, steps, list(patch_size), normalise=return_prob)
+    net.train(was_training)
+    return (mask, agg) if return_prob else mask
+
+
+def compute_dice(predict: torch.Tensor, target: torch.Tensor, ignore_index: int = 0, smooth: float = 1e-5) -> float:
+    """Hard-mask Dice over foreground classes (trainer.py:891-945); metric tail, host sync, not on the hot path."""
+    op = torch.argmax(predict.float(), dim=1)
+    ot = torch.argmax(target, dim=1)
+    C = target.shape[1]
+    dl = np.ones((C,), dtype=np.float32)
+    for i in range(C):
+        if i == ignore_index:
+            continue
+        a, b = (op == i), (ot == i)
+        if not a.any() and not b.any():
+            continue
+        a = a.float().reshape(a.shape[0], -1)
+        b = b.float().reshape(b.shape[0], -1)
+        d = ((2 * (a * b).sum(1) + smooth) / ((a + b).sum(1) + smooth)).mean()
+        dl[i] = round(d.item(), 4)
+    return float(np.nanmean(dl[1:]))
+
+
+# ----------------------------------------------------------------------------- training
+
+
+def train_step(net, criterion, optimizer, data: torch.Tensor, target: torch.Tensor, use_bf16: bool = True):
+    """One optimizer step, same order as trainer.py:366-380.  `data` / `target` may be pinned host tensors.
+    Returns the loss tensor (device; reading it is the caller's sync)."""
+    dev = next(net.parameters()).device
+    data = data.to(dev, non_blocking=True)
+    target = target.to(dev, non_blocking=True)
+    if use_bf16:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            output = net(data)
+    else:
+        output = net(data)
+    loss = criterion(output, target)
+    optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    optimizer.step()
+    return loss
+
+
+class GradBucketer:
+    """All-reduces (average) contiguous ranges of a flat gradient buffer as soon as backward reports them final.
+
+    `notify(end_offset)` launches an asynchronous all-reduce of flat[prev_end:end_offset]; `finish()` makes the
+    current stream wait for all of them (no host block with NCCL).  Works with any backend (gloo in CPU tests)."""
+
+    def __init__(self, flat: torch.Tensor, group=None, min_bucket_elems: int = 1 << 20):
+        self.flat, self.group, self.min_bucket = flat, group, min_bucket_elems
+        self.world = dist.get_world_size(group)
+        self.prev = 0
+        self.works = []
+        self.ranges: List[Tuple[int, int]] = []
+
+    def notify(self, end: int, force: bool = False):
+        if end - self.prev < self.min_bucket and not force:
+            return
+        if end <= self.prev:
+            return
+        seg = self.flat[self.prev:end]
+        if self.world > 1:
+            if dist.get_backend(self.group) == "nccl":
+                self.works.append(dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+            else:
+                w = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self.works.append((w, seg))
+        self.ranges.append((self.prev, end))
+        self.prev = end
+
+    def finish(self):
+        self.notify(self.flat.numel(), force=True)
+        for w in self.works:
+            if isinstance(w, tuple):
+                w[0].wait()
+                w[1].div_(self.world)
+            else:
+                w.wait()
+        self.works = []
+        self.prev = 0
+
+
+class DataParallelTrainer:
+    """One process per GPU; every rank holds a full replica (11 M parameters) and a batch shard.  Replaces
+    nn.DataParallel (trainer.py:228-229): no per-step parameter broadcast, no output gather, gradients are
+    averaged with NCCL over NVLink while the remaining backward kernels run."""
+
+    def __init__(self, net, criterion, optimizer, use_bf16: bool = True, group=None, min_bucket_elems: int = 1 << 20):
+        self.net, self.criterion, self.optimizer, self.use_bf16, self.group = net, criterion, optimizer, use_bf16, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.min_bucket = min_bucket_elems
+        self._bucketer: Optional[GradBucketer] = None
+        if self.world > 1:
+            for p in net.parameters():          # replicas start identical (rank 0's weights)
+                dist.broadcast(p.data, src=0, group=group)
+            net.grad_sync = self._on_ready
+
+    def _on_ready(self, key: str):
+        arena = self.net._grad_arena()
+        if self._bucketer is None or self._bucketer.flat is not arena.flat:
+            self._bucketer = GradBucketer(arena.flat, self.group, self.min_bucket)
+        idx = arena.order.index(key)
+        end = arena.offsets[arena.order[idx + 1]] if idx + 1 < len(arena.order) else arena.total
+        self._bucketer.notify(end)
+        if idx + 1 == len(arena.order):
+            self._bucketer.finish()
+
+    def step(self, data: torch.Tensor, target: torch.Tensor):
+        return train_step(self.net, self.criterion, self.optimizer, data, target, self.use_bf16)

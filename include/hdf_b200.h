@@ -1,0 +1,161 @@
+/* libhdf_b200.so -- C ABI of the B200-native H-DenseFormer 3D hot path.
+ *
+ * The reference (shijun18/H-DenseFormer) is pure Python over torch/ATen library kernels and has no
+ * FFI of its own; each entry point below names the reference call it replaces
+ * (file:line relative to the reference root).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - activations are channels-last [N, D, H, W, C] with an explicit channel stride `ld*` (elements),
+ *     so any operand may be a channel slice of a pre-allocated concat buffer (replaces torch.cat,
+ *     models/HDenseFormer.py:230,247,249,251);
+ *   - `dtype` selects the activation storage type (HDF_F32 exact path, HDF_BF16 fast path); parameters,
+ *     statistics, token tensors and reductions are always fp32 (fp64 for cross-block sums);
+ *   - kernels are launched asynchronously on `stream` (a cudaStream_t); nothing synchronises, nothing
+ *     allocates: callers own every buffer, workspaces are sized by the *_workspace queries;
+ *   - return value 0 = success, <0 = hdf_status; hdf_last_error_string() describes the last failure
+ *     on the calling thread.  There is no CPU fallback anywhere.
+ */
+#ifndef HDF_B200_H
+#define HDF_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { HDF_OK = 0, HDF_ERR_ARG = -1, HDF_ERR_CUDA = -2, HDF_ERR_ARCH = -3, HDF_ERR_UNSUPPORTED = -4 } hdf_status;
+typedef enum { HDF_F32 = 0, HDF_BF16 = 1 } hdf_dtype;
+
+/* ---- library ---- */
+int hdf_init(int device);                 /* checks compute capability 10.x, caches the SM count */
+int hdf_version(void);
+int hdf_sm_count(void);
+const char* hdf_last_error_string(void);
+
+/* ---- 3x3x3 convolutions (nn.Conv3d k3 p1: models/HDenseFormer.py:151,167; nn.ConvTranspose3d k3 s2 p1 op1:
+ *      :211,215,219; their autograd backward).  mode 0: conv s1 p1; mode 1: transposed conv s2 (gather form);
+ *      mode 2: conv s2 p1 (= input gradient of mode 1).  (Do,Ho,Wo) are OUTPUT dims; input dims follow from
+ *      mode.  w_packed is [27][Cin][Cout] fp32 made by hdf_conv_pack_weights. ---- */
+int hdf_conv_pack_weights(const float* w, float* packed, int A, int B, long long stride_a, long long stride_b, int flip,
+                          void* stream); /* packed[tap][a][b] = w[a*stride_a + b*stride_b + (flip ? 26-tap : tap)] */
+int hdf_conv3d_fwd(int dtype, int mode, const void* x, long long ldx, const float* w_packed, const float* bias, void* y,
+                   long long ldy, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* stream);
+size_t hdf_conv3d_wgrad_workspace(int N, int Do, int Ho, int Wo, int Cin, int Cout);
+/* dw[ci*stride_ci + co*stride_co + tap] (+)= sum_o x[in(o,tap)][ci] * dy[o][co]   (torch weight layouts) */
+int hdf_conv3d_wgrad(int dtype, int mode, const void* x, long long ldx, const void* dy, long long ldy, float* dw,
+                     long long stride_ci, long long stride_co, int N, int Do, int Ho, int Wo, int Cin, int Cout,
+                     void* workspace, size_t ws_bytes, int accumulate, void* stream);
+
+/* ---- tcgen05/TMEM tensor-core path for the same convolutions (bf16 activations, fp32 accumulate).
+ *      Returns HDF_ERR_UNSUPPORTED for shapes it does not take; callers then use the SIMT entry above. ---- */
+int hdf_tc_supported(int mode, int Cin, int Cout);
+size_t hdf_tc_pack_bytes(int Cin, int Cout);
+int hdf_tc_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, long long stride_ci, long long stride_co,
+                        int flip, void* stream); /* packed[tap][co][ci] bf16 (K-major B operand per tap) */
+int hdf_tc_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
+                      int N, int D, int H, int W, int Cin, int Cout, double* stats_partial, void* stream);
+size_t hdf_tc_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout);
+int hdf_tc_conv3d_wgrad(const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
+                        long long stride_co, int N, int D, int H, int W, int Cin, int Cout, void* workspace,
+                        size_t ws_bytes, int accumulate, void* stream);
+
+/* ---- patch embedding (nn.Conv3d k16 s16 + position_embeddings + Dropout: models/HDenseFormer.py:115-119,
+ *      133-138).  img is the caller's NCDHW fp32 batch; tokens are [B*ntok, E] fp32 rows (ld = ldo). ---- */
+int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, int H, int W, const float* weight,
+                        const float* bias, const float* pos, float* out, long long ldo, int E, float p,
+                        unsigned long long seed, unsigned call_id, void* stream);
+size_t hdf_patch_embed_wgrad_workspace(int B, int D, int H, int W, int E);
+int hdf_patch_embed_wgrad(const float* img, int B, int Mch, int modality, int D, int H, int W, const float* dtok,
+                          long long ldd, float* dweight, int E, void* workspace, size_t ws_bytes, int accumulate,
+                          void* stream);
+int hdf_posemb_grad(const float* dtok, long long ld, float* dpos, int B, int ntok, int E, int accumulate, void* stream);
+
+/* ---- token GEMMs (nn.Linear: models/HDenseFormer.py:37,40,57,60,85) with fused bias / exact GELU /
+ *      dropout / residual epilogue.  C = epi(A[M,K] @ op(B)); op(B)=B^T for B [N,K] when b_is_nk. ---- */
+int hdf_gemm_rowmajor(const float* A, long long lda, const float* Bm, long long ldb, int b_is_nk, float* C, long long ldc,
+                      int M, int N, int K, const float* bias, const float* residual, long long ldr, float* pre, int act,
+                      float p, unsigned long long seed, unsigned call_id, int accumulate, void* stream);
+size_t hdf_gemm_at_b_workspace(int M, int N, int K);
+int hdf_gemm_at_b(const float* A, long long lda, const float* Bm, long long ldb, float* C, int M, int N, int K,
+                  void* workspace, size_t ws_bytes, int accumulate, void* stream); /* C[M,N] (+)= A[K,M]^T B[K,N] */
+int hdf_act_dropout_bwd(const float* dy, long long ldd, const float* pre, float* dz, long long ldz, int M, int N, int act,
+                        float p, unsigned long long seed, unsigned call_id, void* stream);
+int hdf_add_rows_f32(float* dst, long long ldd, const float* src, long long lds, long long rows, int C, int accumulate,
+                     void* stream);
+
+/* ---- LayerNorm (PreNorm, models/HDenseFormer.py:11-17) and attention (Dense_Attention, :47-75; heads of
+ *      dim 4, qkv rows = [q | k | v], softmax never materialised) ---- */
+int hdf_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float* out, long long ldo,
+                      float* mean, float* rstd, int M, int C, float eps, void* stream);
+size_t hdf_layernorm_bwd_workspace(int M, int C);
+int hdf_layernorm_bwd(const float* dy, long long ldd, const float* x, long long ldx, const float* mean, const float* rstd,
+                      const float* gamma, float* dx, long long ldo, int accumulate_dx, float* dgamma, float* dbeta,
+                      int accumulate_params, int M, int C, void* workspace, size_t ws_bytes, void* stream);
+int hdf_attention_fwd(const float* qkv, long long ld, float* o, long long ldo, float* lse, int B, int N, int H, float scale,
+                      void* stream);
+int hdf_attention_bwd(const float* qkv, long long ld, const float* o, long long ldo, const float* dout, long long lddo,
+                      const float* lse, float* dqkv, long long ldg, int B, int N, int H, float scale, void* stream);
+
+/* ---- InstanceNorm3d (+affine) + ReLU (+ residual add) (BasicConv3d / UpConv: models/HDenseFormer.py:152-158,
+ *      168-169; the "+ at3" adds at :238-244) ---- */
+size_t hdf_reduce_workspace(int N, long long V, int C);
+int hdf_instnorm_stats(int dtype, const void* y, long long ldy, int N, long long V, int C, float eps, float* mean,
+                       float* rstd, void* workspace, size_t ws_bytes, void* stream);
+int hdf_instnorm_apply(int dtype, const void* y, long long ldy, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, const void* residual, long long ldr, void* out, long long ldo, int N,
+                       long long V, int C, int relu, void* stream);
+int hdf_instnorm_bwd(int dtype, const void* dout, long long ldd, const void* y, long long ldy, const float* mean,
+                     const float* rstd, const float* gamma, const float* beta, void* dy, long long ldo, int N, long long V,
+                     int C, int relu, float* s1, float* s2, float* dgamma, float* dbeta, int accumulate_params,
+                     void* workspace, size_t ws_bytes, void* stream);
+int hdf_colsum(int dtype, const void* x, long long ld, long long rows, int C, float* out, int accumulate, void* workspace,
+               size_t ws_bytes, void* stream);
+
+/* ---- pooling / upsampling / element-wise (nn.MaxPool3d(2,2): models/HDenseFormer.py:199,203,207;
+ *      F.interpolate trilinear x2 align_corners=False: :174) ---- */
+int hdf_maxpool2_fwd(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Do, int Ho, int Wo,
+                     int C, void* stream);
+int hdf_maxpool2_bwd(int dtype, const void* x, long long ldx, const void* dpool, long long ldp, void* dx, long long lddx,
+                     int N, int Do, int Ho, int Wo, int C, int accumulate, void* stream);
+int hdf_upsample2_fwd(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Di, int Hi, int Wi,
+                      int C, void* stream);
+int hdf_upsample2_bwd(int dtype, const void* dout, long long ldd, void* dx, long long lddx, int N, int Di, int Hi, int Wi,
+                      int C, int accumulate, void* stream);
+int hdf_add_(int dtype, void* dst, long long ldd, const void* src, long long lds, long long rows, int C, void* stream);
+int hdf_copy_rows(int dtype, void* dst, long long ldd, const void* src, long long lds, long long rows, int C, void* stream);
+int hdf_cast_rows_from_f32(int dtype, const float* src, long long lds, void* dst, long long ldd, long long rows, int C,
+                           void* stream);
+int hdf_cast_rows_to_f32(int dtype, const void* src, long long lds, float* dst, long long ldd, long long rows, int C,
+                         void* stream);
+int hdf_ncdhw_to_cl(int dtype, const float* x, void* out, long long ldo, int N, int C, long long V, void* stream);
+
+/* ---- 1x1x1 heads (nn.Conv3d k1: models/HDenseFormer.py:223-227,246-253); logits are NCDHW ---- */
+int hdf_head_fwd(int dtype, const void* a, long long lda, const float* w, const float* b, void* out, int N, long long V,
+                 int C, int ncls, void* stream);
+size_t hdf_head_bwd_workspace(int N, long long V, int C, int ncls);
+int hdf_head_bwd(int dtype, const void* g, const void* a, long long lda, const float* w, void* da, long long ldd,
+                 float* dw, float* db, int N, long long V, int C, int ncls, int accumulate_da, int accumulate_params,
+                 void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- loss (CEPlusDice / DeepSuperloss: loss/combine_loss.py:25-35,72-79; DiceLoss: loss/dice_loss.py:26-41,
+ *      70-87; CrossentropyLoss: loss/cross_entropy.py:10-22).  One call per deep-supervision level. ---- */
+size_t hdf_loss_sums_bytes(int B, int C);
+int hdf_loss_level_fwd(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
+                       int Hl, int Wl, int level_stride, int ignore_index, int has_ignore, float smooth, float level_weight,
+                       float ce_weight, float dice_weight, double* sums, float* out_level /* [3]: loss, ce, dice */,
+                       float* total, void* stream);
+int hdf_loss_level_bwd(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
+                       int Hl, int Wl, int level_stride, int ignore_index, int has_ignore, float smooth, float level_weight,
+                       float ce_weight, float dice_weight, const double* sums, const float* grad_out, void* dlogits,
+                       void* stream);
+
+/* ---- sliding-window inference (trainer.py:560-582; cal_steps :595-618 stays host code).
+ *      steps_* are HOST arrays of window starts; the count map is analytic, never stored. ---- */
+int hdf_sw_accumulate(int dtype, const void* logits, float* agg, int C, int X, int Y, int Z, int x0, int y0, int z0, int px,
+                      int py, int pz, void* stream);
+int hdf_sw_finalize(float* agg, long long* mask, int C, int X, int Y, int Z, const int* steps_x, int nx, const int* steps_y,
+                    int ny, const int* steps_z, int nz, int patch_x, int patch_y, int patch_z, int normalise, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDF_B200_H */

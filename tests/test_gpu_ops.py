@@ -1,0 +1,264 @@
+"""Per-kernel parity on the GPU, through the C ABI (hdenseformer_b200.ops -> libhdf_b200.so), against plain
+torch fp32 ops of the same semantics (the reference's building blocks).  fp32 path tolerance 1e-4 relative
+(north_star), bf16 storage path 2e-2."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from hdenseformer_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+DEV = "cuda"
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12)).item()
+
+
+def to_cl(x, dt):  # NCDHW -> NDHWC
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(dt)
+
+
+def from_cl(x):
+    return x.float().permute(0, 4, 1, 2, 3).contiguous()
+
+
+@pytest.fixture(autouse=True)
+def _init():
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    torch.manual_seed(0)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cin,cout,size", [(2, 16, (8, 12, 10)), (16, 32, (9, 9, 9)), (32, 16, (6, 10, 18)), (3, 8, (5, 7, 6))])
+def test_conv3d_k3_fwd_dgrad_wgrad(dt, cin, cout, size):
+    x = torch.randn(2, cin, *size, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, 3, device=DEV) / math.sqrt(27 * cin)
+    b = torch.randn(cout, device=DEV)
+    xq = to_cl(x, dt)
+    xr = from_cl(xq).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv3d(xr, wr, b, padding=1)
+    wp = ops.conv_pack(w, cin, cout, 27, cin * 27, False)
+    y = torch.empty((2, *size, cout), dtype=dt, device=DEV)
+    ops.conv3d_fwd(xq, wp, b, y, 0)
+    assert rel(from_cl(y), ref) < TOL[dt]
+    g = torch.randn_like(ref)
+    gq = to_cl(g, dt)
+    ref.backward(from_cl(gq))
+    wpd = ops.conv_pack(w, cout, cin, cin * 27, 27, True)
+    dx = torch.empty((2, *size, cin), dtype=dt, device=DEV)
+    ops.conv3d_fwd(gq, wpd, None, dx, 0)
+    assert rel(from_cl(dx), xr.grad) < TOL[dt]
+    dw = torch.zeros_like(w)
+    ops.conv3d_wgrad(xq, gq, dw, 27, cin * 27, 0)
+    assert rel(dw, wr.grad) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_conv_transpose_fwd_dgrad_wgrad(dt):
+    cin, cout, size = 16, 8, (4, 6, 5)
+    x = torch.randn(2, cin, *size, device=DEV)
+    w = torch.randn(cin, cout, 3, 3, 3, device=DEV) / math.sqrt(8 * cin)
+    b = torch.randn(cout, device=DEV)
+    xq = to_cl(x, dt)
+    xr = from_cl(xq).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv_transpose3d(xr, wr, b, stride=2, padding=1, output_padding=1)
+    osz = tuple(2 * s for s in size)
+    wp = ops.conv_pack(w, cin, cout, cout * 27, 27, False)
+    buf = torch.zeros((2, *osz, cout + 8), dtype=dt, device=DEV)      # write into a channel slice
+    y = buf[..., 8:]
+    ops.conv3d_fwd(xq, wp, b, y, 1)
+    assert rel(from_cl(y), ref) < TOL[dt]
+    assert buf[..., :8].abs().max().item() == 0
+    g = torch.randn_like(ref)
+    gq = to_cl(g, dt)
+    ref.backward(from_cl(gq))
+    wpd = ops.conv_pack(w, cout, cin, 27, cout * 27, False)
+    dx = torch.empty((2, *size, cin), dtype=dt, device=DEV)
+    ops.conv3d_fwd(gq, wpd, None, dx, 2)
+    assert rel(from_cl(dx), xr.grad) < TOL[dt]
+    dw = torch.zeros_like(w)
+    ops.conv3d_wgrad(xq, gq, dw, cout * 27, 27, 1)
+    assert rel(dw, wr.grad) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("affine,res", [(True, True), (False, False)])
+def test_instnorm_relu_fwd_bwd(dt, affine, res):
+    C, size = 16, (6, 5, 7)
+    y = torch.randn(2, C, *size, device=DEV) * 2 + 0.5
+    r = torch.randn(2, C, *size, device=DEV)
+    gm = (1 + 0.1 * torch.randn(C, device=DEV)) if affine else None
+    bt = (0.1 * torch.randn(C, device=DEV)) if affine else None
+    yq, rq = to_cl(y, dt), to_cl(r, dt)
+    yr = from_cl(yq).requires_grad_(True)
+    gr = gm.clone().requires_grad_(True) if affine else None
+    br = bt.clone().requires_grad_(True) if affine else None
+    ref = F.relu(F.instance_norm(yr, weight=gr, bias=br, eps=1e-5))
+    if res:
+        ref = ref + from_cl(rq)
+    mean, rstd = ops.instnorm_stats(yq)
+    out = torch.empty_like(yq)
+    ops.instnorm_apply(yq, mean, rstd, gm, bt, out, residual=rq if res else None, relu=True)
+    assert rel(from_cl(out), ref) < TOL[dt]
+    g = torch.randn_like(ref)
+    gq = to_cl(g, dt)
+    ref.backward(from_cl(gq))
+    dg = torch.zeros(C, device=DEV) if affine else None
+    db = torch.zeros(C, device=DEV) if affine else None
+    dy = ops.instnorm_bwd(gq, yq, mean, rstd, gm, bt, dg, db, relu=True)
+    assert rel(from_cl(dy), yr.grad) < (1e-3 if dt == torch.float32 else 3e-2)
+    if affine:
+        assert rel(dg, gr.grad) < TOL[dt] * 5 and rel(db, br.grad) < TOL[dt] * 5
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_maxpool_and_upsample(dt):
+    C, size = 8, (4, 6, 8)
+    x = torch.randn(2, C, *size, device=DEV)
+    x[:, :, :2] = 0.0   # ties: first max in scan order must win, like torch
+    xq = to_cl(x, dt)
+    xr = from_cl(xq).requires_grad_(True)
+    ref = F.max_pool3d(xr, 2, 2)
+    out = torch.empty((2, 2, 3, 4, C), dtype=dt, device=DEV)
+    ops.maxpool2_fwd(xq, out)
+    assert torch.equal(from_cl(out), ref.detach())
+    g = to_cl(torch.randn_like(ref), dt)
+    ref.backward(from_cl(g))
+    dx = torch.full_like(xq, 7.0)
+    ops.maxpool2_bwd(xq, g, dx, False)
+    assert torch.equal(from_cl(dx), xr.grad)
+    base = to_cl(torch.randn_like(x), dt)
+    dx2 = base.clone()
+    ops.maxpool2_bwd(xq, g, dx2, True)
+    assert rel(from_cl(dx2), from_cl(base) + xr.grad) < TOL[dt]
+    # trilinear x2
+    xr2 = from_cl(xq).requires_grad_(True)
+    ref = F.interpolate(xr2, scale_factor=2, mode="trilinear", align_corners=False)
+    up = torch.empty((2, 8, 12, 16, C), dtype=dt, device=DEV)
+    ops.upsample2_fwd(xq, up)
+    assert rel(from_cl(up), ref) < TOL[dt]
+    g = to_cl(torch.randn_like(ref), dt)
+    ref.backward(from_cl(g))
+    dxu = torch.empty_like(xq)
+    ops.upsample2_bwd(g, dxu, False)
+    assert rel(from_cl(dxu), xr2.grad) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,ncls", [(16, 2), (32, 4), (256, 3)])
+def test_head_fwd_bwd(dt, C, ncls):
+    size = (4, 5, 6)
+    a = torch.randn(2, C, *size, device=DEV)
+    w = torch.randn(ncls, C, 1, 1, 1, device=DEV) / math.sqrt(C)
+    b = torch.randn(ncls, device=DEV)
+    aq = to_cl(a, dt)
+    ar = from_cl(aq).requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv3d(ar, wr, br)
+    out = ops.head_fwd(aq, w.view(ncls, C), b)
+    assert out.shape == ref.shape and rel(out, ref) < TOL[dt]
+    g = torch.randn_like(ref).to(dt)
+    ref.backward(g.float())
+    base = to_cl(torch.randn_like(a), dt)
+    da = base.clone()
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    ops.head_bwd(g.contiguous(), aq, w.view(ncls, C), da, dw, db, True)
+    assert rel(from_cl(da), from_cl(base) + ar.grad) < TOL[dt]
+    assert rel(dw, wr.grad) < TOL[dt] and rel(db, br.grad) < TOL[dt]
+
+
+def test_token_gemm_layernorm_attention():
+    R, B = 2 * 27, 2
+    x = torch.randn(R, 160, device=DEV)
+    W = torch.randn(32, 96, device=DEV) / 10
+    b = torch.randn(32, device=DEV)
+    out = torch.empty(R, 32, device=DEV)
+    pre = torch.empty(R, 32, device=DEV)
+    res = torch.randn(R, 32, device=DEV)
+    ops.gemm(x[:, :96], W, True, out, bias=b, residual=res, pre=pre, act=1)
+    z = x[:, :96] @ W.t() + b
+    assert rel(pre, z) < 1e-5 and rel(out, F.gelu(z) + res) < 1e-5
+    dW = torch.zeros(32, 96, device=DEV)
+    g = torch.randn(R, 32, device=DEV)
+    ops.gemm_at_b(g, x[:, :96], dW, accumulate=False)
+    assert rel(dW, g.t() @ x[:, :96]) < 1e-5
+    dx = torch.zeros(R, 160, device=DEV)
+    ops.gemm(g, W, False, dx[:, :96])
+    assert rel(dx[:, :96], g @ W) < 1e-5 and dx[:, 96:].abs().max().item() == 0
+    # gelu backward
+    dz = ops.act_dropout_bwd(g, pre, 1, 0.0, 0, 0)
+    zr = z.clone().requires_grad_(True)
+    F.gelu(zr).backward(g)
+    assert rel(dz, zr.grad) < 1e-5
+    # layer norm
+    h = torch.randn(R, 32, device=DEV, requires_grad=True)
+    gm, bt = torch.randn(32, device=DEV, requires_grad=True), torch.randn(32, device=DEV, requires_grad=True)
+    ref = F.layer_norm(h, (32,), gm, bt, 1e-5)
+    o, m, r = ops.layernorm_fwd(h.detach(), gm.detach(), bt.detach())
+    assert rel(o, ref) < 1e-5
+    ref.backward(g)
+    dh = torch.empty(R, 32, device=DEV)
+    dgm, dbt = torch.zeros(32, device=DEV), torch.zeros(32, device=DEV)
+    ops.layernorm_bwd(g, h.detach(), m, r, gm.detach(), dh, False, dgm, dbt)
+    assert rel(dh, h.grad) < 1e-4 and rel(dgm, gm.grad) < 1e-4 and rel(dbt, bt.grad) < 1e-4
+    # attention, 8 heads of dim 4
+    for N in (27, 200):
+        qkv = torch.randn(B * N, 96, device=DEV, requires_grad=True)
+        q, k, v = (t.reshape(B, N, 8, 4).permute(0, 2, 1, 3) for t in qkv.chunk(3, -1))
+        att = ((q @ k.transpose(-1, -2)) * 0.5).softmax(-1)
+        ref = (att @ v).permute(0, 2, 1, 3).reshape(B * N, 32)
+        o, lse = ops.attention_fwd(qkv.detach(), B, N, 8, 0.5)
+        assert rel(o, ref) < 1e-5
+        go = torch.randn_like(ref)
+        ref.backward(go)
+        dqkv = ops.attention_bwd(qkv.detach(), o, go, lse, B, N, 8, 0.5)
+        assert rel(dqkv, qkv.grad) < 1e-4
+
+
+def test_dropout_statistics_and_mask_replay():
+    R, N = 4096, 64
+    a = torch.ones(R, 8, device=DEV)
+    W = torch.ones(N, 8, device=DEV)
+    outs = []
+    for cid in (1, 2):
+        out = torch.empty(R, N, device=DEV)
+        ops.gemm(a, W, True, out, p=0.5, seed=1234, call_id=cid)
+        outs.append(out)
+        keep = (out != 0).float().mean().item()
+        assert abs(keep - 0.5) < 0.01                      # keep rate
+        assert torch.all((out == 0) | (out == 16.0))       # inverted-dropout scale 2
+    assert 0.45 < ((outs[0] != 0) == (outs[1] != 0)).float().mean().item() < 0.55   # call sites independent
+    g = torch.ones(R, N, device=DEV)
+    dz = ops.act_dropout_bwd(g, None, 0, 0.5, 1234, 1)
+    assert torch.equal(dz != 0, outs[0] != 0)              # backward replays the forward mask
+
+
+def test_patch_embed_fwd_wgrad():
+    B, Mch, size, E = 2, 2, (32, 16, 48), 32
+    img = torch.randn(B, Mch, *size, device=DEV)
+    w = (torch.randn(E, 1, 16, 16, 16, device=DEV) / 64).requires_grad_(True)
+    b = torch.randn(E, device=DEV)
+    ntok = 2 * 1 * 3
+    pos = torch.randn(1, ntok, E, device=DEV)
+    out = torch.zeros(B * ntok, E + 16, device=DEV)
+    ops.patch_embed_fwd(img, 1, w.detach(), b, pos, out[:, :E], 0.0, 0, 0)
+    ref = F.conv3d(img[:, 1:2], w, b, stride=16).flatten(2).transpose(1, 2) + pos
+    assert rel(out[:, :E], ref.reshape(B * ntok, E)) < 1e-5
+    g = torch.randn(B * ntok, E, device=DEV)
+    ref.reshape(B * ntok, E).backward(g)
+    dw = torch.zeros_like(w)
+    ops.patch_embed_wgrad(img, 1, g, dw)
+    assert rel(dw, w.grad) < 1e-5
+    dpos = torch.zeros_like(pos)
+    ops.posemb_grad(g, dpos, B, ntok, E)
+    assert rel(dpos, g.view(B, ntok, E).sum(0, keepdim=True)) < 1e-5
