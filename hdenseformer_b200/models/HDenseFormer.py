@@ -81,9 +81,8 @@ def _default_init(key: str, shape: tuple) -> torch.Tensor:
 
 class _HDFFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, dtype, training, seed, *params):
+    def forward(ctx, module, x, dtype, training, seed, need_grad, *params):
         P = dict(zip(module._keys, params))
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         outs, saved = module._engine.forward(P, x, dtype, training, seed, save=need_grad)
         ctx.module, ctx.saved, ctx.P = module, saved, P
         ctx.set_materialize_grads(False)
@@ -96,7 +95,7 @@ class _HDFFunction(torch.autograd.Function):
         arena.zero_()
         m._engine.backward(ctx.P, arena.views, ctx.saved, list(gouts), on_grads_ready=m._on_grads_ready)
         ctx.saved = None
-        return (None, None, None, None, None, *[arena.views[k] for k in m._keys])
+        return (None, None, None, None, None, None, *[arena.views[k] for k in m._keys])
 
 
 class HDenseFormer(nn.Module):
@@ -173,7 +172,8 @@ class HDenseFormer(nn.Module):
         params = [p for _, p in self.named_parameters()]
         self._step += 1
         seed = (torch.initial_seed() * 1000003 + self._step) & 0x7FFFFFFFFFFFFFFF
-        outs = _HDFFunction.apply(self, x, self._resolve_dtype(), self.training, seed, *params)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        outs = _HDFFunction.apply(self, x, self._resolve_dtype(), self.training, seed, need_grad, *params)
         return list(outs)
 
 
