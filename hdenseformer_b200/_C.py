@@ -29,7 +29,7 @@ def declared_symbols(header: str = HEADER):
     src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(int|size_t|const char\*)\s+(hdf_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(int|size_t|const char\*|unsigned long long)\s+(hdf_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
         argtypes = []
         if args and args != "void":
@@ -40,7 +40,7 @@ def declared_symbols(header: str = HEADER):
                 else:
                     ty = " ".join(a.split()[:-1])
                     argtypes.append(_CTYPE[ty])
-        restype = {"int": C.c_int, "size_t": C.c_size_t, "const char*": C.c_char_p}[ret]
+        restype = {"int": C.c_int, "size_t": C.c_size_t, "const char*": C.c_char_p, "unsigned long long": C.c_ulonglong}[ret]
         out[name] = (restype, argtypes)
     return out
 

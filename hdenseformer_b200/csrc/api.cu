@@ -7,6 +7,7 @@
 static thread_local char g_err[512] = "";
 static int g_sm_count = 0;
 static int g_device = -1;
+unsigned long long g_hdf_launches = 0;
 
 void hdf_set_error(const char* fmt, ...) {
   va_list ap;
@@ -50,5 +51,7 @@ int hdf_init(int device) {
 }
 
 int hdf_sm_count(void) { return g_sm_count; }
+
+unsigned long long hdf_launch_count(void) { return g_hdf_launches; }
 
 }  // extern "C"

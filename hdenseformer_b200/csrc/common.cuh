@@ -8,6 +8,7 @@
 #include "../../include/hdf_b200.h"
 
 void hdf_set_error(const char* fmt, ...);
+extern unsigned long long g_hdf_launches;   // kernels launched by this library (bench.py "gpu_launches")
 
 #define HDF_REQUIRE(cond, ...)                 \
   do {                                         \
@@ -19,6 +20,7 @@ void hdf_set_error(const char* fmt, ...);
 
 #define HDF_LAUNCH_CHECK(name)                                                     \
   do {                                                                             \
+    ++g_hdf_launches;                                                              \
     cudaError_t e__ = cudaGetLastError();                                          \
     if (e__ != cudaSuccess) {                                                      \
       hdf_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));       \

@@ -84,6 +84,8 @@ class Engine:
         """x: [N,D,H,W,Cin] view; w: torch-layout weight; out: [N,Do,Ho,Wo,Cout] view."""
         if mode == 0:    # Conv3d weight [Cout, Cin, 27]
             Cout, Cin = w.shape[0], w.shape[1]
+            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(0, Cin, Cout):
+                return ops.tc_conv3d_fwd(x, ops.tc_pack(w, Cin, Cout, 27, Cin * 27, False), bias, out)
             wp = ops.conv_pack(w, Cin, Cout, 27, Cin * 27, False)
         else:            # ConvTranspose3d weight [Cin, Cout, 27]
             Cin, Cout = w.shape[0], w.shape[1]
@@ -95,6 +97,9 @@ class Engine:
         mode 1 (transposed conv) -> strided conv (mode 2)."""
         if mode == 0:
             Cout, Cin = w.shape[0], w.shape[1]
+            if self.use_tc and dy.dtype == torch.bfloat16 and ops.tc_supported(0, Cout, Cin):
+                # GEMM K = Cout (channels of dy), GEMM N = Cin: packed[tap][ci][co] = w[co][ci][26-tap]
+                return ops.tc_conv3d_fwd(dy, ops.tc_pack(w, Cout, Cin, Cin * 27, 27, True), None, out)
             wp = ops.conv_pack(w, Cout, Cin, Cin * 27, 27, True)      # packed[tap][co][ci] = w[co][ci][26-tap]
             return ops.conv3d_fwd(dy, wp, None, out, 0)
         Cin, Cout = w.shape[0], w.shape[1]

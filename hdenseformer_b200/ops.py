@@ -81,6 +81,27 @@ def conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, stride_ci:
                                      Ho, Wo, Cin, Cout, _p(ws), ws.numel(), int(accumulate), _s()), "conv3d_wgrad")
 
 
+# ----------------------------------------------------------------------------- tcgen05 conv path (bf16)
+def tc_supported(mode: int, Cin: int, Cout: int) -> bool:
+    return bool(_lib().hdf_tc_supported(mode, Cin, Cout))
+
+
+def tc_pack(w: torch.Tensor, Cin: int, Cout: int, stride_ci: int, stride_co: int, flip: bool) -> torch.Tensor:
+    """packed[tap][co][ci] bf16 = w[ci*stride_ci + co*stride_co + (26-tap if flip else tap)]"""
+    out = torch.empty((27, Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    _C.check(_lib().hdf_tc_pack_weights(_p(w), _p(out), Cin, Cout, stride_ci, stride_co, int(flip), _s()), "tc_pack")
+    return out
+
+
+def tc_conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor):
+    N, D, H, W, Cout = out.shape
+    Cin = x.shape[-1]
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    _C.check(_lib().hdf_tc_conv3d_fwd(_p(x), _ld(x), _p(wp), _p(bias), _p(out), _ld(out), N, D, H, W, Cin, Cout, None, _s()),
+             "tc_conv3d_fwd")
+    return out
+
+
 # ----------------------------------------------------------------------------- instance norm & friends
 def instnorm_stats(y: torch.Tensor, eps: float = 1e-5):
     N, C = y.shape[0], y.shape[-1]

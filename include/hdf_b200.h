@@ -29,6 +29,7 @@ typedef enum { HDF_F32 = 0, HDF_BF16 = 1 } hdf_dtype;
 int hdf_init(int device);                 /* checks compute capability 10.x, caches the SM count */
 int hdf_version(void);
 int hdf_sm_count(void);
+unsigned long long hdf_launch_count(void);   /* kernels launched by this library so far (this process) */
 const char* hdf_last_error_string(void);
 
 /* ---- 3x3x3 convolutions (nn.Conv3d k3 p1: models/HDenseFormer.py:151,167; nn.ConvTranspose3d k3 s2 p1 op1:

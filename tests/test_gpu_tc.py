@@ -1,0 +1,77 @@
+"""tcgen05 / TMA implicit-GEMM convolution (csrc/tc_conv.cu) against torch's fp32 conv on bf16-rounded operands.
+Products of bf16 numbers are exact in fp32, so only the accumulation order differs: tolerance 2e-3 of max|y|
+before the bf16 output rounding (2^-8 relative) -> 1e-2 overall."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from hdenseformer_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+
+DEV = "cuda"
+
+CASES = [
+    # cin, cout, (D,H,W), N
+    (16, 16, (8, 8, 8), 1),          # SW32, full tiles
+    (32, 32, (16, 8, 16), 2),        # SW64
+    (64, 64, (8, 16, 16), 1),        # SW128
+    (32, 64, (9, 9, 9), 2),          # partial tiles in every dim
+    (64, 32, (18, 18, 18), 1),
+    (128, 128, (6, 10, 12), 1),      # 2 K-chunks
+    (256, 128, (9, 9, 9), 1),        # 4 K-chunks
+    (128, 256, (4, 6, 10), 2),       # N = 256 (TMEM 512 cols)
+    (48, 80, (5, 7, 11), 1),         # KC = 16 with 3 chunks, odd N
+]
+
+
+@pytest.mark.parametrize("cin,cout,size,N", CASES)
+def test_tc_conv_fwd_matches_torch(cin, cout, size, N):
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    assert ops.tc_supported(0, cin, cout)
+    torch.manual_seed(cin * 1000 + cout)
+    x = torch.randn(N, *size, cin + 16, device=DEV).to(torch.bfloat16)
+    xs = x[..., 8:8 + cin]                                   # channel slice input (ld != C)
+    w = (torch.randn(cout, cin, 3, 3, 3, device=DEV) / math.sqrt(27 * cin))
+    b = torch.randn(cout, device=DEV)
+    wq = w.to(torch.bfloat16).float()
+    ref = F.conv3d(xs.float().permute(0, 4, 1, 2, 3), wq, b, padding=1).permute(0, 2, 3, 4, 1)
+    buf = torch.zeros(N, *size, cout + 8, dtype=torch.bfloat16, device=DEV)
+    y = buf[..., 8:]                                         # channel slice output
+    wp = ops.tc_pack(w, cin, cout, 27, cin * 27, False)
+    assert torch.equal(wp[5].float(), wq[:, :, 0, 1, 2])
+    ops.tc_conv3d_fwd(xs, wp, b, y)
+    torch.cuda.synchronize()
+    err = ((y.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-2, err
+    assert buf[..., :8].abs().max().item() == 0              # nothing written outside the slice
+    # dgrad form: flipped taps, swapped channels == gradient of conv wrt its input
+    g = torch.randn(N, *size, cout, device=DEV).to(torch.bfloat16)
+    xr = xs.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    F.conv3d(xr, wq, None, padding=1).backward(g.float().permute(0, 4, 1, 2, 3))
+    if ops.tc_supported(0, cout, cin):
+        wpd = ops.tc_pack(w, cout, cin, cin * 27, 27, True)
+        dx = torch.empty(N, *size, cin, dtype=torch.bfloat16, device=DEV)
+        ops.tc_conv3d_fwd(g, wpd, None, dx)
+        refdx = xr.grad.permute(0, 2, 3, 4, 1)
+        err = ((dx.float() - refdx).abs().max() / refdx.abs().max()).item()
+        assert err < 1e-2, err
+
+
+def test_tc_conv_matches_simt_path_large():
+    """72^3 x 32->32: thousands of tiles through the persistent scheduler, vs our own SIMT kernel."""
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    torch.manual_seed(1)
+    x = torch.randn(1, 72, 72, 72, 32, device=DEV).to(torch.bfloat16)
+    w = torch.randn(32, 32, 3, 3, 3, device=DEV) / math.sqrt(27 * 32)
+    y1 = torch.empty(1, 72, 72, 72, 32, dtype=torch.bfloat16, device=DEV)
+    y2 = torch.empty_like(y1)
+    ops.tc_conv3d_fwd(x, ops.tc_pack(w, 32, 32, 27, 32 * 27, False), None, y1)
+    ops.conv3d_fwd(x, ops.conv_pack(w.to(torch.bfloat16).float(), 32, 32, 27, 32 * 27, False), None, y2, 0)
+    torch.cuda.synchronize()
+    err = ((y1.float() - y2.float()).abs().max() / y2.float().abs().max()).item()
+    assert err < 1e-2, err
