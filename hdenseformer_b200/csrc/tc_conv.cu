@@ -258,6 +258,173 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   }
 }
 
+
+// ----------------------------------------------------------------------------- weight-gradient kernel
+//   dW[tap][ci][co] = sum_v X[v + off(tap)][ci] * dY[v][co]
+// GEMM per CTA: K = voxels of this CTA's slab (KV = 128 or 64 per pipeline chunk), N = Cout (the dY tile, MN-major
+// B operand), M = 128 rows made of SPG = 128/CW shifted/offset input sub-tiles [KV x CW channels] stacked along M
+// through the descriptor's leading-byte-offset (CW = min(Cin, 64)): for Cin = 32 one MMA covers 4 taps, for
+// Cin = 64 two taps, for Cin >= 128 one tap's 128-channel slice.  Each such "group" owns Cout TMEM columns; a CTA
+// handles one pass = up to 512/Cout groups, over one slab of voxel chunks (split-K); fp32 partials go to the
+// workspace and a second kernel reduces them deterministically into the torch-layout gradient.
+struct TcWgradParams {
+  int N, D, H, W, Cin, Cout;
+  int TD, TH, TW, nTd, nTh, nTw;
+  int num_chunks, chunks_per_slab, num_slabs;
+  int KV;                  // voxels per chunk (rows of every smem tile)
+  int CW, SPG, sub_per_tap, total_sub, total_groups, groups_per_pass;
+  int CWn, nsub_b;
+  int a_stages;
+  uint32_t a_sub_bytes, a_stage_bytes, b_sub_bytes, b_stage_bytes;
+  uint32_t a_layout, a_sbo, b_layout, b_sbo;
+  uint32_t tmem_cols;
+  float* partial;          // [num_slabs][27][Cin][Cout]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmdy, const TcWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t b_base = smem_base + p.a_stages * p.a_stage_bytes;
+  const uint32_t bar_base = b_base + 2 * p.b_stage_bytes;
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (p.a_stages + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * p.a_stages + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * p.a_stages + 2 + s); };
+  const uint32_t accfull = bar_base + 8u * (2 * p.a_stages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.a_stages + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int slab = blockIdx.x, pass = blockIdx.y;
+  const int g_begin = pass * p.groups_per_pass;
+  const int g_end = min(p.total_groups, g_begin + p.groups_per_pass);
+  const int c_begin = slab * p.chunks_per_slab;
+  const int c_end = min(p.num_chunks, c_begin + p.chunks_per_slab);
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmx); tma_prefetch_desc(&tmdy); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    mbar_init(accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int tiles_per_n = p.nTd * p.nTh * p.nTw;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int s = 0; uint32_t ph = 0;
+      int bs = 0; uint32_t bph = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        const int n = c / tiles_per_n;
+        int r = c - n * tiles_per_n;
+        const int tw = r % p.nTw; r /= p.nTw;
+        const int th = r % p.nTh;
+        const int td = r / p.nTh;
+        const int d0 = td * p.TD, h0 = th * p.TH, w0 = tw * p.TW;
+        mbar_wait(bempty(bs), bph ^ 1u);
+        mbar_expect_tx(bfull(bs), p.b_sub_bytes * p.nsub_b);
+        for (int j = 0; j < p.nsub_b; ++j)
+          tma_load_5d(b_base + bs * p.b_stage_bytes + j * p.b_sub_bytes, &tmdy, bfull(bs), j * p.CWn, w0, h0, d0, n);
+        if (++bs == 2) { bs = 0; bph ^= 1u; }
+        for (int g = g_begin; g < g_end; ++g) {
+          const int u0 = g * p.SPG;
+          const int nsub = min(p.SPG, p.total_sub - u0);
+          mbar_wait(aempty(s), ph ^ 1u);
+          mbar_expect_tx(afull(s), p.a_sub_bytes * nsub);
+          for (int j = 0; j < nsub; ++j) {
+            const int u = u0 + j;
+            const int tap = u / p.sub_per_tap, ch0 = (u - tap * p.sub_per_tap) * p.CW;
+            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+            tma_load_5d(smem_base + s * p.a_stage_bytes + j * p.a_sub_bytes, &tmx, afull(s), ch0, w0 + kw - 1, h0 + kh - 1,
+                        d0 + kd - 1, n);
+          }
+          if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc(128, p.Cout, 1, 1);   // both operands MN-major (K = voxel rows)
+      int s = 0; uint32_t ph = 0;
+      int bs = 0; uint32_t bph = 0;
+      const int ksteps = p.KV / 16;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(bfull(bs), bph);
+        tc_fence_after();
+        const uint64_t bdesc = umma_desc(b_base + bs * p.b_stage_bytes, p.b_sub_bytes, p.b_sbo, p.b_layout);
+        for (int g = g_begin; g < g_end; ++g) {
+          mbar_wait(afull(s), ph);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc(smem_base + s * p.a_stage_bytes, p.a_sub_bytes, p.a_sbo, p.a_layout);
+          const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_begin) * p.Cout);
+          for (int k = 0; k < ksteps; ++k)   // advance 16 voxel rows = 2 swizzle-atom groups = 2*SBO bytes
+            umma_bf16(d_tmem, adesc + (uint64_t)((2u * p.a_sbo * k) >> 4), bdesc + (uint64_t)((2u * p.b_sbo * k) >> 4), idesc,
+                      (c != c_begin) || (k != 0));
+          umma_commit(aempty(s));
+          if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(bempty(bs));
+        if (++bs == 2) { bs = 0; bph ^= 1u; }
+      }
+      umma_commit(accfull);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: accumulators -> fp32 partials =====
+    const int q = warp - 4;
+    const int m = q * 32 + lane;
+    mbar_wait(accfull, 0);
+    tc_fence_after();
+    for (int g = g_begin; g < g_end; ++g) {
+      const int u = g * p.SPG + m / p.CW;
+      const bool valid = u < p.total_sub;
+      const int tap = valid ? u / p.sub_per_tap : 0;
+      const int ci = valid ? (u - tap * p.sub_per_tap) * p.CW + m % p.CW : 0;
+      float* dst = p.partial + (((long long)slab * 27 + tap) * p.Cin + ci) * p.Cout;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_begin) * p.Cout);
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// partials [S][27][Cin][Cout] -> g[ci*sci + co*sco + tap] (+= if accumulate); fixed summation order
+__global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ g, int S, int Cin, int Cout,
+                                       long long sci, long long sco, int accumulate) {
+  const long long per = 27ll * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < S; ++z) s += part[z * per + i];
+    const int co = i % Cout;
+    const int ci = (i / Cout) % Cin;
+    const int tap = i / ((long long)Cin * Cout);
+    float* q = g + ci * sci + co * sco + tap;
+    *q = accumulate ? (*q + s) : s;
+  }
+}
+
 // ----------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -396,11 +563,114 @@ int hdf_tc_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, c
   return HDF_OK;
 }
 
-size_t hdf_tc_wgrad_workspace(int, int, int, int, int, int) { return 0; }
-int hdf_tc_conv3d_wgrad(const void*, long long, const void*, long long, float*, long long, long long, int, int, int, int, int,
-                        int, void*, size_t, int, void*) {
-  hdf_set_error("hdf_tc_conv3d_wgrad: not built yet");
-  return HDF_ERR_UNSUPPORTED;
+static int wgrad_ok(int c) { return c == 16 || c == 32 || (c % 64 == 0 && c >= 64); }
+
+int hdf_tc_wgrad_supported(int Cin, int Cout) { return wgrad_ok(Cin) && wgrad_ok(Cout) && Cout <= 256; }
+
+static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradParams& p) {
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.KV = (Cout > 128) ? 64 : 128;
+  // tile = KV voxels
+  {
+    long long best = -1; p.TD = p.TH = p.TW = 1;
+    for (int tw = 1; tw <= p.KV; tw *= 2)
+      for (int th = 1; th * tw <= p.KV; th *= 2) {
+        const int td = p.KV / (tw * th);
+        const long long tiles = (long long)cdiv(D, td) * cdiv(H, th) * cdiv(W, tw);
+        if (best < 0 || tiles < best || (tiles == best && tw > p.TW)) { best = tiles; p.TD = td; p.TH = th; p.TW = tw; }
+      }
+  }
+  p.nTd = cdiv(D, p.TD); p.nTh = cdiv(H, p.TH); p.nTw = cdiv(W, p.TW);
+  p.num_chunks = N * p.nTd * p.nTh * p.nTw;
+  p.CW = Cin < 64 ? Cin : 64;
+  p.SPG = 128 / p.CW;
+  p.sub_per_tap = Cin / p.CW;
+  p.total_sub = 27 * p.sub_per_tap;
+  p.total_groups = cdiv(p.total_sub, p.SPG);
+  p.groups_per_pass = 512 / Cout;
+  if (p.groups_per_pass > p.total_groups) p.groups_per_pass = p.total_groups;
+  p.CWn = Cout < 64 ? Cout : 64;
+  p.nsub_b = Cout / p.CWn;
+  p.a_sub_bytes = (uint32_t)p.KV * p.CW * 2;
+  p.a_stage_bytes = p.a_sub_bytes * p.SPG;          // = KV*256 bytes, multiple of 1024
+  p.b_sub_bytes = (uint32_t)p.KV * p.CWn * 2;
+  p.b_stage_bytes = (p.b_sub_bytes * p.nsub_b + 1023u) & ~1023u;
+  p.a_stages = (int)((200u * 1024u - 2u * p.b_stage_bytes) / p.a_stage_bytes);
+  if (p.a_stages > 6) p.a_stages = 6;
+  if (p.a_stages < 2) p.a_stages = 2;
+  const int ia = p.CW * 2, ib = p.CWn * 2;
+  p.a_layout = ia == 128 ? 2u : ia == 64 ? 4u : 6u;
+  p.b_layout = ib == 128 ? 2u : ib == 64 ? 4u : 6u;
+  p.a_sbo = 8u * ia;
+  p.b_sbo = 8u * ib;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.groups_per_pass * Cout)) cols *= 2;
+  p.tmem_cols = cols;
+  const int passes = cdiv(p.total_groups, p.groups_per_pass);
+  // split-K: ~2 CTAs per SM in total, at least 8 chunks per slab
+  int slabs = cdiv(2 * hdf_sm_count_cached(), passes);
+  const int max_slabs = p.num_chunks / 8 > 0 ? p.num_chunks / 8 : 1;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  p.chunks_per_slab = cdiv(p.num_chunks, slabs);
+  p.num_slabs = cdiv(p.num_chunks, p.chunks_per_slab);
+  return passes;
+}
+
+size_t hdf_tc_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout) {
+  if (!hdf_tc_wgrad_supported(Cin, Cout)) return 0;
+  TcWgradParams p;
+  tc_wgrad_plan(N, D, H, W, Cin, Cout, p);
+  return (size_t)p.num_slabs * 27 * Cin * Cout * sizeof(float);
+}
+
+int hdf_tc_conv3d_wgrad(const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
+                        long long stride_co, int N, int D, int H, int W, int Cin, int Cout, void* workspace,
+                        size_t ws_bytes, int accumulate, void* stream) {
+  if (!hdf_tc_wgrad_supported(Cin, Cout)) {
+    hdf_set_error("hdf_tc_conv3d_wgrad: unsupported channels Cin=%d Cout=%d", Cin, Cout);
+    return HDF_ERR_UNSUPPORTED;
+  }
+  HDF_REQUIRE(x && dy && dw && workspace, "hdf_tc_conv3d_wgrad: null pointer");
+  HDF_REQUIRE((ldx % 8 == 0) && (ldy % 8 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0),
+              "hdf_tc_conv3d_wgrad: operands must be 16-byte aligned with channel strides multiple of 8");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { hdf_set_error("hdf_tc_conv3d_wgrad: cuTensorMapEncodeTiled unavailable"); return HDF_ERR_CUDA; }
+  TcWgradParams p;
+  const int passes = tc_wgrad_plan(N, D, H, W, Cin, Cout, p);
+  HDF_REQUIRE(ws_bytes >= (size_t)p.num_slabs * 27 * Cin * Cout * sizeof(float), "hdf_tc_conv3d_wgrad: workspace too small");
+  p.partial = (float*)workspace;
+  CUtensorMap tmx, tmdy;
+  for (int which = 0; which < 2; ++which) {
+    const void* base = which == 0 ? x : dy;
+    const long long ld = which == 0 ? ldx : ldy;
+    const int C = which == 0 ? Cin : Cout;
+    const int cw = which == 0 ? p.CW : p.CWn;
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t gstr[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2, (cuuint64_t)D * H * W * ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)cw, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TD, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(which == 0 ? &tmx : &tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { hdf_set_error("hdf_tc_conv3d_wgrad: encode failed: %d", (int)r); return HDF_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + 2 * (size_t)p.b_stage_bytes + 1024 + 8 * (2 * p.a_stages + 6) + 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) { hdf_set_error("hdf_tc_conv3d_wgrad: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
+    configured = true;
+  }
+  HDF_REQUIRE(smem <= 227 * 1024, "hdf_tc_conv3d_wgrad: smem plan too large (%zu)", smem);
+  dim3 grid(p.num_slabs, passes);
+  tc_conv_wgrad_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmdy, p);
+  HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad");
+  const long long per = 27ll * Cin * Cout;
+  tc_wgrad_reduce_kernel<<<min(2048, cdiv(per, 256)), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, p.num_slabs,
+                                                                                     Cin, Cout, stride_ci, stride_co, accumulate);
+  HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad/reduce");
+  return HDF_OK;
 }
 
 }  // extern "C"

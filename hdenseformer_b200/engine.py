@@ -108,7 +108,9 @@ class Engine:
 
     def _conv_wgrad(self, x, dy, dw, mode=0):
         if mode == 0:    # dw [Cout, Cin, 27]
-            Cin = dw.shape[1]
+            Cout, Cin = dw.shape[0], dw.shape[1]
+            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_wgrad_supported(Cin, Cout):
+                return ops.tc_conv3d_wgrad(x, dy, dw, 27, Cin * 27)
             ops.conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
         else:            # dw [Cin, Cout, 27]
             Cout = dw.shape[1]

@@ -102,6 +102,18 @@ def tc_conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
+def tc_wgrad_supported(Cin: int, Cout: int) -> bool:
+    return bool(_lib().hdf_tc_wgrad_supported(Cin, Cout))
+
+
+def tc_conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, stride_ci: int, stride_co: int, accumulate=False):
+    N, D, H, W, Cout = dy.shape
+    Cin = x.shape[-1]
+    ws = Workspace.get(_lib().hdf_tc_wgrad_workspace(N, D, H, W, Cin, Cout))
+    _C.check(_lib().hdf_tc_conv3d_wgrad(_p(x), _ld(x), _p(dy), _ld(dy), _p(dw), stride_ci, stride_co, N, D, H, W, Cin, Cout,
+                                        _p(ws), ws.numel(), int(accumulate), _s()), "tc_conv3d_wgrad")
+
+
 # ----------------------------------------------------------------------------- instance norm & friends
 def instnorm_stats(y: torch.Tensor, eps: float = 1e-5):
     N, C = y.shape[0], y.shape[-1]

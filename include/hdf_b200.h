@@ -54,6 +54,7 @@ int hdf_tc_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, lo
                         int flip, void* stream); /* packed[tap][co][ci] bf16 (K-major B operand per tap) */
 int hdf_tc_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
                       int N, int D, int H, int W, int Cin, int Cout, double* stats_partial, void* stream);
+int hdf_tc_wgrad_supported(int Cin, int Cout);
 size_t hdf_tc_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout);
 int hdf_tc_conv3d_wgrad(const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
                         long long stride_co, int N, int D, int H, int W, int Cin, int Cout, void* workspace,

@@ -75,3 +75,36 @@ def test_tc_conv_matches_simt_path_large():
     torch.cuda.synchronize()
     err = ((y1.float() - y2.float()).abs().max() / y2.float().abs().max()).item()
     assert err < 1e-2, err
+
+
+WG_CASES = [
+    (16, 16, (8, 8, 8), 1),       # SW32, 8 taps per MMA group
+    (32, 32, (16, 16, 24), 2),    # 4 taps per group, several slabs
+    (64, 32, (9, 9, 9), 2),       # partial tiles; 14 groups in one pass (448 TMEM columns)
+    (32, 64, (8, 12, 20), 1),
+    (64, 64, (10, 16, 16), 1),    # 2 passes
+    (128, 128, (6, 10, 12), 1),   # 7 passes
+    (256, 128, (9, 9, 9), 1),     # two 128-channel groups per tap
+    (128, 256, (4, 6, 10), 2),    # KV = 64 chunks, N = 256
+]
+
+
+@pytest.mark.parametrize("cin,cout,size,N", WG_CASES)
+def test_tc_conv_wgrad_matches_torch(cin, cout, size, N):
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    assert ops.tc_wgrad_supported(cin, cout)
+    torch.manual_seed(cin * 7 + cout)
+    xb = torch.randn(N, *size, cin + 8, device=DEV).to(torch.bfloat16)
+    x = xb[..., 8:]
+    gb = torch.randn(N, *size, cout + 16, device=DEV).to(torch.bfloat16)
+    g = gb[..., :cout]
+    w = torch.zeros(cout, cin, 3, 3, 3, device=DEV, requires_grad=True)
+    F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, None, padding=1).backward(g.float().permute(0, 4, 1, 2, 3))
+    dw = torch.full((cout, cin, 3, 3, 3), 3.0, device=DEV)
+    ops.tc_conv3d_wgrad(x, g, dw, 27, cin * 27, accumulate=False)
+    torch.cuda.synchronize()
+    err = ((dw - w.grad).abs().max() / w.grad.abs().max()).item()
+    assert err < 1e-3, err
+    ops.tc_conv3d_wgrad(x, g, dw, 27, cin * 27, accumulate=True)
+    err = ((dw - 2 * w.grad).abs().max() / w.grad.abs().max()).item()
+    assert err < 2e-3, err
