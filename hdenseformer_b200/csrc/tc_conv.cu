@@ -13,6 +13,7 @@
 // The kernel is persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
 // The same kernel computes the input gradient (dgrad) with tap-flipped, channel-swapped packed weights.
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -115,8 +116,23 @@ __host__ __device__ inline uint32_t umma_idesc(int M, int N, int a_mn_major, int
 }
 
 // ----------------------------------------------------------------------------- forward / dgrad kernel
+// Tap table: the same kernel runs (mode 0) conv k3 s1 p1 -- 1 class, 27 taps, input coord = j + (k-1);
+// (mode 1) transposed conv k3 s2 p1 op1 -- 8 output-parity classes with 1/2/4/8 taps over the INPUT grid,
+// input coord = j + {0,1}, output coord = 2j + parity; (mode 2) conv k3 s2 p1 (input gradient of
+// mode 1) -- 27 taps, input coord = 2j + (k-1) through a TMA map with element stride 2.
+struct TcTaps {
+  signed char dd[64], dh[64], dw[64];
+  signed char widx[64];
+  signed char first[9];
+  signed char pd[8], ph[8], pw[8];
+  int ncls;
+};
+
 struct TcConvParams {
-  int N, D, H, W, Cin, Cout;
+  int N, D, H, W, Cin, Cout;   // D,H,W: base grid the tiles walk over
+  int Do, Ho, Wo;              // output tensor dims
+  int in_scale, out_scale;
+  TcTaps taps;
   int TD, TH, TW;
   int nTd, nTh, nTw;
   int num_tiles;
@@ -162,28 +178,31 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int kiters = 27 * p.kchunks;
   const int tiles_per_n = p.nTd * p.nTh * p.nTw;
+  const int tiles_per_cls = p.N * tiles_per_n;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_n;
-        int r = tile - n * tiles_per_n;
+        const int cls = tile / tiles_per_cls;
+        int r = tile - cls * tiles_per_cls;
+        const int n = r / tiles_per_n;
+        r -= n * tiles_per_n;
         const int tw = r % p.nTw; r /= p.nTw;
         const int th = r % p.nTh;
         const int td = r / p.nTh;
-        const int d0 = td * p.TD, h0 = th * p.TH, w0 = tw * p.TW;
+        const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TW * p.in_scale;
+        const int e0 = p.taps.first[cls];
+        const int kiters = (p.taps.first[cls + 1] - e0) * p.kchunks;
         for (int it = 0; it < kiters; ++it) {
-          const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          const int e = e0 + it / p.kchunks, kc = it % p.kchunks;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), p.a_bytes + p.b_bytes);
           const uint32_t a_dst = smem_base + s * p.stage_bytes;
-          tma_load_5d(a_dst, &tmx, full_bar(s), kc * p.KC, w0 + kw - 1, h0 + kh - 1, d0 + kd - 1, n);
-          tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, tap * p.Cout);
+          tma_load_5d(a_dst, &tmx, full_bar(s), kc * p.KC, w0 + p.taps.dw[e], h0 + p.taps.dh[e], d0 + p.taps.dd[e], n);
+          tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, (int)p.taps.widx[e] * p.Cout);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -195,6 +214,8 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t accph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int cls = tile / tiles_per_cls;
+        const int kiters = (p.taps.first[cls + 1] - p.taps.first[cls]) * p.kchunks;
         mbar_wait(tempty_bar(acc), accph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
@@ -221,14 +242,18 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     const int mw = m % p.TW, mh = (m / p.TW) % p.TH, md = m / (p.TW * p.TH);
     int acc = 0; uint32_t accph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n = tile / tiles_per_n;
-      int r = tile - n * tiles_per_n;
+      const int cls = tile / tiles_per_cls;
+      int r = tile - cls * tiles_per_cls;
+      const int n = r / tiles_per_n;
+      r -= n * tiles_per_n;
       const int tw = r % p.nTw; r /= p.nTw;
       const int th = r % p.nTh;
       const int td = r / p.nTh;
       const int d = td * p.TD + md, h = th * p.TH + mh, w = tw * p.TW + mw;
       const bool valid = d < p.D && h < p.H && w < p.W;
-      bf16* yrow = p.y + ((((long long)n * p.D + d) * p.H + h) * p.W + w) * p.ldy;
+      const int od = d * p.out_scale + p.taps.pd[cls], oh = h * p.out_scale + p.taps.ph[cls],
+                ow = w * p.out_scale + p.taps.pw[cls];
+      bf16* yrow = p.y + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.ldy;
       mbar_wait(tfull_bar(acc), accph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout);
@@ -275,6 +300,7 @@ struct TcWgradParams {
   int CW, SPG, sub_per_tap, total_sub, total_groups, groups_per_pass;
   int CWn, nsub_b;
   int a_stages;
+  int a_scale;             // 1: A-side coords j + (k-1); 2: A-side is the 2x-resolution tensor, coords 2j + (k-1)
   uint32_t a_sub_bytes, a_stage_bytes, b_sub_bytes, b_stage_bytes;
   uint32_t a_layout, a_sbo, b_layout, b_sbo;
   uint32_t tmem_cols;
@@ -328,6 +354,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
         const int th = r % p.nTh;
         const int td = r / p.nTh;
         const int d0 = td * p.TD, h0 = th * p.TH, w0 = tw * p.TW;
+        const int ad0 = d0 * p.a_scale - 1, ah0 = h0 * p.a_scale - 1, aw0 = w0 * p.a_scale - 1;
         mbar_wait(bempty(bs), bph ^ 1u);
         mbar_expect_tx(bfull(bs), p.b_sub_bytes * p.nsub_b);
         for (int j = 0; j < p.nsub_b; ++j)
@@ -342,8 +369,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
             const int u = u0 + j;
             const int tap = u / p.sub_per_tap, ch0 = (u - tap * p.sub_per_tap) * p.CW;
             const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-            tma_load_5d(smem_base + s * p.a_stage_bytes + j * p.a_sub_bytes, &tmx, afull(s), ch0, w0 + kw - 1, h0 + kh - 1,
-                        d0 + kd - 1, n);
+            tma_load_5d(smem_base + s * p.a_stage_bytes + j * p.a_sub_bytes, &tmx, afull(s), ch0, aw0 + kw, ah0 + kh, ad0 + kd, n);
           }
           if (++s == p.a_stages) { s = 0; ph ^= 1u; }
         }
@@ -459,6 +485,38 @@ void pick_tile(int D, int H, int W, int& TD, int& TH, int& TW) {
     }
 }
 
+void build_taps(int mode, TcTaps& t) {
+  memset(&t, 0, sizeof(t));
+  if (mode == 0 || mode == 2) {
+    t.ncls = 1;
+    t.first[0] = 0; t.first[1] = 27;
+    for (int k = 0; k < 27; ++k) {
+      t.dd[k] = (signed char)(k / 9 - 1); t.dh[k] = (signed char)((k / 3) % 3 - 1); t.dw[k] = (signed char)(k % 3 - 1);
+      t.widx[k] = (signed char)k;
+    }
+  } else {
+    // per dim: parity 0 -> tap k=1 reads input j ; parity 1 -> k=0 reads j+1, k=2 reads j   (o = 2 i - 1 + k)
+    t.ncls = 8;
+    int e = 0;
+    for (int c = 0; c < 8; ++c) {
+      const int pd = (c >> 2) & 1, ph = (c >> 1) & 1, pw = c & 1;
+      t.first[c] = (signed char)e;
+      t.pd[c] = (signed char)pd; t.ph[c] = (signed char)ph; t.pw[c] = (signed char)pw;
+      const int kd_n = pd ? 2 : 1, kh_n = ph ? 2 : 1, kw_n = pw ? 2 : 1;
+      for (int a = 0; a < kd_n; ++a)
+        for (int b = 0; b < kh_n; ++b)
+          for (int cc = 0; cc < kw_n; ++cc) {
+            const int kd = pd ? (a == 0 ? 0 : 2) : 1, kh = ph ? (b == 0 ? 0 : 2) : 1, kw = pw ? (cc == 0 ? 0 : 2) : 1;
+            t.dd[e] = (signed char)(kd == 0 ? 1 : 0); t.dh[e] = (signed char)(kh == 0 ? 1 : 0);
+            t.dw[e] = (signed char)(kw == 0 ? 1 : 0);
+            t.widx[e] = (signed char)(kd * 9 + kh * 3 + kw);
+            ++e;
+          }
+    }
+    t.first[8] = (signed char)e;   // 27
+  }
+}
+
 __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cin, int Cout, long long sci,
                                long long sco, int flip) {
   const long long total = 27ll * Cin * Cout;
@@ -475,7 +533,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
 extern "C" {
 
 int hdf_tc_supported(int mode, int Cin, int Cout) {
-  if (mode != 0) return 0;
+  if (mode < 0 || mode > 2) return 0;
   if (Cin % 16 != 0 || Cin < 16) return 0;
   if (Cout % 16 != 0 || Cout < 16 || Cout > 256) return 0;
   return 1;
@@ -494,10 +552,9 @@ int hdf_tc_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, lo
   return HDF_OK;
 }
 
-int hdf_tc_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
-                      int N, int D, int H, int W, int Cin, int Cout, double* stats_partial, void* stream) {
-  (void)stats_partial;
-  if (!hdf_tc_supported(0, Cin, Cout)) {
+int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y,
+                      long long ldy, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* stream) {
+  if (!hdf_tc_supported(mode, Cin, Cout)) {
     hdf_set_error("hdf_tc_conv3d_fwd: unsupported channels Cin=%d Cout=%d", Cin, Cout);
     return HDF_ERR_UNSUPPORTED;
   }
@@ -508,10 +565,19 @@ int hdf_tc_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, c
   if (!enc) { hdf_set_error("hdf_tc_conv3d_fwd: cuTensorMapEncodeTiled unavailable"); return HDF_ERR_CUDA; }
 
   TcConvParams p;
+  if (mode == 1) HDF_REQUIRE(((Do | Ho | Wo) & 1) == 0, "hdf_tc_conv3d_fwd: transposed conv needs even output dims");
+  // base grid the tiles walk over: output grid (modes 0, 2) or input grid (mode 1)
+  const int D = mode == 1 ? Do / 2 : Do, H = mode == 1 ? Ho / 2 : Ho, W = mode == 1 ? Wo / 2 : Wo;
+  // input tensor dims
+  const int Di = mode == 2 ? 2 * Do : D, Hi = mode == 2 ? 2 * Ho : H, Wi = mode == 2 ? 2 * Wo : W;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.Do = Do; p.Ho = Ho; p.Wo = Wo;
+  p.in_scale = mode == 2 ? 2 : 1;
+  p.out_scale = mode == 1 ? 2 : 1;
+  build_taps(mode, p.taps);
   pick_tile(D, H, W, p.TD, p.TH, p.TW);
   p.nTd = cdiv(D, p.TD); p.nTh = cdiv(H, p.TH); p.nTw = cdiv(W, p.TW);
-  p.num_tiles = N * p.nTd * p.nTh * p.nTw;
+  p.num_tiles = p.taps.ncls * N * p.nTd * p.nTh * p.nTw;
   p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
   p.kchunks = Cin / p.KC;
   p.a_bytes = 128u * p.KC * 2u;
@@ -530,11 +596,12 @@ int hdf_tc_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, c
 
   CUtensorMap tmx, tmw;
   {
-    cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-    cuuint64_t gstr[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2,
-                          (cuuint64_t)D * H * W * ldx * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TD, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint32_t es = (cuuint32_t)p.in_scale;
+    cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)N};
+    cuuint64_t gstr[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)Wi * ldx * 2, (cuuint64_t)Hi * Wi * ldx * 2,
+                          (cuuint64_t)Di * Hi * Wi * ldx * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)p.TW * es, (cuuint32_t)p.TH * es, (cuuint32_t)p.TD * es, 1};
+    cuuint32_t estr[5] = {1, es, es, es, 1};
     CUresult r = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(inner), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -565,7 +632,11 @@ int hdf_tc_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, c
 
 static int wgrad_ok(int c) { return c == 16 || c == 32 || (c % 64 == 0 && c >= 64); }
 
-int hdf_tc_wgrad_supported(int Cin, int Cout) { return wgrad_ok(Cin) && wgrad_ok(Cout) && Cout <= 256; }
+// the N side of the GEMM (dy channels for mode 0, x channels for the transposed conv) must fit one MMA (<= 256)
+int hdf_tc_wgrad_supported(int mode, int Cin, int Cout) {
+  if (mode != 0 && mode != 1) return 0;
+  return wgrad_ok(Cin) && wgrad_ok(Cout) && (mode == 0 ? Cout : Cin) <= 256;
+}
 
 static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradParams& p) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -617,18 +688,19 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   return passes;
 }
 
-size_t hdf_tc_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout) {
-  if (!hdf_tc_wgrad_supported(Cin, Cout)) return 0;
+size_t hdf_tc_wgrad_workspace(int mode, int N, int Do, int Ho, int Wo, int Cin, int Cout) {
+  if (!hdf_tc_wgrad_supported(mode, Cin, Cout)) return 0;
   TcWgradParams p;
-  tc_wgrad_plan(N, D, H, W, Cin, Cout, p);
+  if (mode == 0) tc_wgrad_plan(N, Do, Ho, Wo, Cin, Cout, p);
+  else tc_wgrad_plan(N, Do / 2, Ho / 2, Wo / 2, Cout, Cin, p);
   return (size_t)p.num_slabs * 27 * Cin * Cout * sizeof(float);
 }
 
-int hdf_tc_conv3d_wgrad(const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
-                        long long stride_co, int N, int D, int H, int W, int Cin, int Cout, void* workspace,
+int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
+                        long long stride_co, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* workspace,
                         size_t ws_bytes, int accumulate, void* stream) {
-  if (!hdf_tc_wgrad_supported(Cin, Cout)) {
-    hdf_set_error("hdf_tc_conv3d_wgrad: unsupported channels Cin=%d Cout=%d", Cin, Cout);
+  if (!hdf_tc_wgrad_supported(mode, Cin, Cout)) {
+    hdf_set_error("hdf_tc_conv3d_wgrad: unsupported mode/channels mode=%d Cin=%d Cout=%d", mode, Cin, Cout);
     return HDF_ERR_UNSUPPORTED;
   }
   HDF_REQUIRE(x && dy && dw && workspace, "hdf_tc_conv3d_wgrad: null pointer");
@@ -636,20 +708,33 @@ int hdf_tc_conv3d_wgrad(const void* x, long long ldx, const void* dy, long long 
               "hdf_tc_conv3d_wgrad: operands must be 16-byte aligned with channel strides multiple of 8");
   EncodeTiledFn enc = get_encode();
   if (!enc) { hdf_set_error("hdf_tc_conv3d_wgrad: cuTensorMapEncodeTiled unavailable"); return HDF_ERR_CUDA; }
+  // A side = the shifted operand whose taps are stacked along M; B side = the fixed tile (GEMM N)
+  //   mode 0: A = x (shift k-1),            B = dy ; base grid = output grid
+  //   mode 1: A = dy (2x res, shift 2j+k-1), B = x  ; base grid = input grid        (dW[ci][co][k] = sum_i x[i] dy[2i-1+k])
+  const int D = mode == 0 ? Do : Do / 2, H = mode == 0 ? Ho : Ho / 2, W = mode == 0 ? Wo : Wo / 2;
+  const void* a_ptr = mode == 0 ? x : dy;
+  const void* b_ptr = mode == 0 ? dy : x;
+  const long long a_ld = mode == 0 ? ldx : ldy, b_ld = mode == 0 ? ldy : ldx;
+  const int Ca = mode == 0 ? Cin : Cout, Cb = mode == 0 ? Cout : Cin;
+  const long long sa = mode == 0 ? stride_ci : stride_co, sb = mode == 0 ? stride_co : stride_ci;
   TcWgradParams p;
-  const int passes = tc_wgrad_plan(N, D, H, W, Cin, Cout, p);
+  const int passes = tc_wgrad_plan(N, D, H, W, Ca, Cb, p);
+  p.a_scale = mode == 0 ? 1 : 2;
   HDF_REQUIRE(ws_bytes >= (size_t)p.num_slabs * 27 * Cin * Cout * sizeof(float), "hdf_tc_conv3d_wgrad: workspace too small");
   p.partial = (float*)workspace;
   CUtensorMap tmx, tmdy;
   for (int which = 0; which < 2; ++which) {
-    const void* base = which == 0 ? x : dy;
-    const long long ld = which == 0 ? ldx : ldy;
-    const int C = which == 0 ? Cin : Cout;
+    const void* base = which == 0 ? a_ptr : b_ptr;
+    const long long ld = which == 0 ? a_ld : b_ld;
+    const int C = which == 0 ? Ca : Cb;
     const int cw = which == 0 ? p.CW : p.CWn;
-    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-    cuuint64_t gstr[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2, (cuuint64_t)D * H * W * ld * 2};
-    cuuint32_t box[5] = {(cuuint32_t)cw, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TD, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint32_t es = which == 0 ? (cuuint32_t)p.a_scale : 1u;
+    const int Dt = D * (int)es, Ht = H * (int)es, Wt = W * (int)es;
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)Dt, (cuuint64_t)N};
+    cuuint64_t gstr[4] = {(cuuint64_t)ld * 2, (cuuint64_t)Wt * ld * 2, (cuuint64_t)Ht * Wt * ld * 2,
+                          (cuuint64_t)Dt * Ht * Wt * ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)cw, (cuuint32_t)p.TW * es, (cuuint32_t)p.TH * es, (cuuint32_t)p.TD * es, 1};
+    cuuint32_t estr[5] = {1, es, es, es, 1};
     CUresult r = enc(which == 0 ? &tmx : &tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -668,7 +753,7 @@ int hdf_tc_conv3d_wgrad(const void* x, long long ldx, const void* dy, long long 
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad");
   const long long per = 27ll * Cin * Cout;
   tc_wgrad_reduce_kernel<<<min(2048, cdiv(per, 256)), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, p.num_slabs,
-                                                                                     Cin, Cout, stride_ci, stride_co, accumulate);
+                                                                                     Ca, Cb, sa, sb, accumulate);
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad/reduce");
   return HDF_OK;
 }

@@ -89,6 +89,8 @@ class Engine:
             wp = ops.conv_pack(w, Cin, Cout, 27, Cin * 27, False)
         else:            # ConvTranspose3d weight [Cin, Cout, 27]
             Cin, Cout = w.shape[0], w.shape[1]
+            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(1, Cin, Cout):
+                return ops.tc_conv3d_fwd(x, ops.tc_pack(w, Cin, Cout, Cout * 27, 27, False), bias, out, mode=1)
             wp = ops.conv_pack(w, Cin, Cout, Cout * 27, 27, False)
         return ops.conv3d_fwd(x, wp, bias, out, mode)
 
@@ -103,17 +105,22 @@ class Engine:
             wp = ops.conv_pack(w, Cout, Cin, Cin * 27, 27, True)      # packed[tap][co][ci] = w[co][ci][26-tap]
             return ops.conv3d_fwd(dy, wp, None, out, 0)
         Cin, Cout = w.shape[0], w.shape[1]
+        if self.use_tc and dy.dtype == torch.bfloat16 and ops.tc_supported(2, Cout, Cin):
+            # strided conv over dy: GEMM K = Cout, N = Cin; packed[tap][n=ci][k=co] = w[ci][co][tap]
+            return ops.tc_conv3d_fwd(dy, ops.tc_pack(w, Cout, Cin, 27, Cout * 27, False), None, out, mode=2)
         wp = ops.conv_pack(w, Cout, Cin, 27, Cout * 27, False)         # packed[tap][co][ci] = w[ci][co][tap]
         return ops.conv3d_fwd(dy, wp, None, out, 2)
 
     def _conv_wgrad(self, x, dy, dw, mode=0):
         if mode == 0:    # dw [Cout, Cin, 27]
             Cout, Cin = dw.shape[0], dw.shape[1]
-            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_wgrad_supported(Cin, Cout):
-                return ops.tc_conv3d_wgrad(x, dy, dw, 27, Cin * 27)
+            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_wgrad_supported(0, Cin, Cout):
+                return ops.tc_conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
             ops.conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
         else:            # dw [Cin, Cout, 27]
-            Cout = dw.shape[1]
+            Cin, Cout = dw.shape[0], dw.shape[1]
+            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_wgrad_supported(1, Cin, Cout):
+                return ops.tc_conv3d_wgrad(x, dy, dw, Cout * 27, 27, 1)
             ops.conv3d_wgrad(x, dy, dw, Cout * 27, 27, 1)
 
     # ------------------------------------------------------------------ BasicConv3d / UpConv

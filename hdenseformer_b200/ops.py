@@ -93,25 +93,26 @@ def tc_pack(w: torch.Tensor, Cin: int, Cout: int, stride_ci: int, stride_co: int
     return out
 
 
-def tc_conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor):
-    N, D, H, W, Cout = out.shape
+def tc_conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, mode: int = 0):
+    N, Do, Ho, Wo, Cout = out.shape
     Cin = x.shape[-1]
     assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
-    _C.check(_lib().hdf_tc_conv3d_fwd(_p(x), _ld(x), _p(wp), _p(bias), _p(out), _ld(out), N, D, H, W, Cin, Cout, None, _s()),
+    _C.check(_lib().hdf_tc_conv3d_fwd(mode, _p(x), _ld(x), _p(wp), _p(bias), _p(out), _ld(out), N, Do, Ho, Wo, Cin, Cout, _s()),
              "tc_conv3d_fwd")
     return out
 
 
-def tc_wgrad_supported(Cin: int, Cout: int) -> bool:
-    return bool(_lib().hdf_tc_wgrad_supported(Cin, Cout))
+def tc_wgrad_supported(mode: int, Cin: int, Cout: int) -> bool:
+    return bool(_lib().hdf_tc_wgrad_supported(mode, Cin, Cout))
 
 
-def tc_conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, stride_ci: int, stride_co: int, accumulate=False):
-    N, D, H, W, Cout = dy.shape
+def tc_conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, stride_ci: int, stride_co: int, mode: int = 0,
+                    accumulate=False):
+    N, Do, Ho, Wo, Cout = dy.shape
     Cin = x.shape[-1]
-    ws = Workspace.get(_lib().hdf_tc_wgrad_workspace(N, D, H, W, Cin, Cout))
-    _C.check(_lib().hdf_tc_conv3d_wgrad(_p(x), _ld(x), _p(dy), _ld(dy), _p(dw), stride_ci, stride_co, N, D, H, W, Cin, Cout,
-                                        _p(ws), ws.numel(), int(accumulate), _s()), "tc_conv3d_wgrad")
+    ws = Workspace.get(_lib().hdf_tc_wgrad_workspace(mode, N, Do, Ho, Wo, Cin, Cout))
+    _C.check(_lib().hdf_tc_conv3d_wgrad(mode, _p(x), _ld(x), _p(dy), _ld(dy), _p(dw), stride_ci, stride_co, N, Do, Ho, Wo, Cin,
+                                        Cout, _p(ws), ws.numel(), int(accumulate), _s()), "tc_conv3d_wgrad")
 
 
 # ----------------------------------------------------------------------------- instance norm & friends

@@ -52,12 +52,12 @@ int hdf_tc_supported(int mode, int Cin, int Cout);
 size_t hdf_tc_pack_bytes(int Cin, int Cout);
 int hdf_tc_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, long long stride_ci, long long stride_co,
                         int flip, void* stream); /* packed[tap][co][ci] bf16 (K-major B operand per tap) */
-int hdf_tc_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
-                      int N, int D, int H, int W, int Cin, int Cout, double* stats_partial, void* stream);
-int hdf_tc_wgrad_supported(int Cin, int Cout);
-size_t hdf_tc_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout);
-int hdf_tc_conv3d_wgrad(const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
-                        long long stride_co, int N, int D, int H, int W, int Cin, int Cout, void* workspace,
+int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y,
+                      long long ldy, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* stream);
+int hdf_tc_wgrad_supported(int mode, int Cin, int Cout);   /* mode 0 or 1 */
+size_t hdf_tc_wgrad_workspace(int mode, int N, int Do, int Ho, int Wo, int Cin, int Cout);
+int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
+                        long long stride_co, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* workspace,
                         size_t ws_bytes, int accumulate, void* stream);
 
 /* ---- patch embedding (nn.Conv3d k16 s16 + position_embeddings + Dropout: models/HDenseFormer.py:115-119,

@@ -92,7 +92,7 @@ WG_CASES = [
 @pytest.mark.parametrize("cin,cout,size,N", WG_CASES)
 def test_tc_conv_wgrad_matches_torch(cin, cout, size, N):
     ops.ensure_init(torch.zeros(1, device=DEV))
-    assert ops.tc_wgrad_supported(cin, cout)
+    assert ops.tc_wgrad_supported(0, cin, cout)
     torch.manual_seed(cin * 7 + cout)
     xb = torch.randn(N, *size, cin + 8, device=DEV).to(torch.bfloat16)
     x = xb[..., 8:]
@@ -101,10 +101,50 @@ def test_tc_conv_wgrad_matches_torch(cin, cout, size, N):
     w = torch.zeros(cout, cin, 3, 3, 3, device=DEV, requires_grad=True)
     F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, None, padding=1).backward(g.float().permute(0, 4, 1, 2, 3))
     dw = torch.full((cout, cin, 3, 3, 3), 3.0, device=DEV)
-    ops.tc_conv3d_wgrad(x, g, dw, 27, cin * 27, accumulate=False)
+    ops.tc_conv3d_wgrad(x, g, dw, 27, cin * 27, 0, accumulate=False)
     torch.cuda.synchronize()
     err = ((dw - w.grad).abs().max() / w.grad.abs().max()).item()
     assert err < 1e-3, err
-    ops.tc_conv3d_wgrad(x, g, dw, 27, cin * 27, accumulate=True)
+    ops.tc_conv3d_wgrad(x, g, dw, 27, cin * 27, 0, accumulate=True)
     err = ((dw - 2 * w.grad).abs().max() / w.grad.abs().max()).item()
     assert err < 2e-3, err
+
+
+CT_CASES = [(32, 16, (4, 6, 8), 2), (64, 32, (9, 9, 9), 1), (128, 64, (5, 6, 7), 1), (256, 128, (4, 4, 6), 1), (64, 32, (18, 18, 18), 1)]
+
+
+@pytest.mark.parametrize("cin,cout,size,N", CT_CASES)
+def test_tc_conv_transpose_fwd_dgrad_wgrad(cin, cout, size, N):
+    """nn.ConvTranspose3d k3 s2 p1 op1 on tensor cores: 8 output-parity classes (fwd), stride-2 TMA gather
+    (dgrad and wgrad)."""
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    torch.manual_seed(cin + cout)
+    x = torch.randn(N, *size, cin, device=DEV).to(torch.bfloat16)
+    w = torch.randn(cin, cout, 3, 3, 3, device=DEV) / math.sqrt(8 * cin)
+    b = torch.randn(cout, device=DEV)
+    wq = w.to(torch.bfloat16).float().requires_grad_(True)
+    xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    ref = F.conv_transpose3d(xr, wq, b, stride=2, padding=1, output_padding=1)
+    osz = tuple(2 * s for s in size)
+    buf = torch.zeros(N, *osz, cout + 8, dtype=torch.bfloat16, device=DEV)
+    y = buf[..., :cout]
+    assert ops.tc_supported(1, cin, cout)
+    ops.tc_conv3d_fwd(x, ops.tc_pack(w, cin, cout, cout * 27, 27, False), b, y, mode=1)
+    torch.cuda.synchronize()
+    refl = ref.detach().permute(0, 2, 3, 4, 1)
+    err = ((y.float() - refl).abs().max() / refl.abs().max()).item()
+    assert err < 1e-2, err
+    assert buf[..., cout:].abs().max().item() == 0
+    g = torch.randn(N, *osz, cout, device=DEV).to(torch.bfloat16)
+    ref.backward(g.float().permute(0, 4, 1, 2, 3))
+    dx = torch.empty(N, *size, cin, dtype=torch.bfloat16, device=DEV)
+    assert ops.tc_supported(2, cout, cin)
+    ops.tc_conv3d_fwd(g, ops.tc_pack(w, cout, cin, 27, cout * 27, False), None, dx, mode=2)
+    refdx = xr.grad.permute(0, 2, 3, 4, 1)
+    err = ((dx.float() - refdx).abs().max() / refdx.abs().max()).item()
+    assert err < 1e-2, err
+    if ops.tc_wgrad_supported(1, cin, cout):
+        dw = torch.zeros_like(w)
+        ops.tc_conv3d_wgrad(x, g, dw, cout * 27, 27, 1)
+        err = ((dw - wq.grad).abs().max() / wq.grad.abs().max()).item()
+        assert err < 1e-3, err
