@@ -518,13 +518,13 @@ void build_taps(int mode, TcTaps& t) {
 }
 
 __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cin, int Cout, long long sci,
-                               long long sco, int flip) {
+                               long long sco, int flip, int cin_valid) {
   const long long total = 27ll * Cin * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ci = i % Cin;
     const int co = (i / Cin) % Cout;
     const int tap = i / ((long long)Cin * Cout);
-    out[i] = __float2bfloat16_rn(w[ci * sci + co * sco + (flip ? 26 - tap : tap)]);
+    out[i] = ci < cin_valid ? __float2bfloat16_rn(w[ci * sci + co * sco + (flip ? 26 - tap : tap)]) : __float2bfloat16_rn(0.f);
   }
 }
 
@@ -541,13 +541,14 @@ int hdf_tc_supported(int mode, int Cin, int Cout) {
 
 size_t hdf_tc_pack_bytes(int Cin, int Cout) { return (size_t)27 * Cin * Cout * sizeof(bf16); }
 
-// packed[tap][co][ci] (bf16) = w[ci*stride_ci + co*stride_co + (flip ? 26-tap : tap)]
+// packed[tap][co][ci] (bf16) = ci < cin_valid ? w[ci*stride_ci + co*stride_co + (flip ? 26-tap : tap)] : 0
+// (cin_valid < Cin zero-pads the K dimension so that 2..4-channel inputs can use the 16-channel TMA/UMMA path)
 int hdf_tc_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, long long stride_ci, long long stride_co,
-                        int flip, void* stream) {
+                        int flip, int cin_valid, void* stream) {
   HDF_REQUIRE(w && packed_bf16, "hdf_tc_pack_weights: null pointer");
   const long long total = 27ll * Cin * Cout;
   tc_pack_kernel<<<min(1024, cdiv(total, 256)), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)packed_bf16, Cin, Cout, stride_ci,
-                                                                              stride_co, flip);
+                                                                              stride_co, flip, cin_valid);
   HDF_LAUNCH_CHECK("hdf_tc_pack_weights");
   return HDF_OK;
 }

@@ -84,8 +84,10 @@ class Engine:
         """x: [N,D,H,W,Cin] view; w: torch-layout weight; out: [N,Do,Ho,Wo,Cout] view."""
         if mode == 0:    # Conv3d weight [Cout, Cin, 27]
             Cout, Cin = w.shape[0], w.shape[1]
-            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(0, Cin, Cout):
-                return ops.tc_conv3d_fwd(x, ops.tc_pack(w, Cin, Cout, 27, Cin * 27, False), bias, out)
+            Cx = x.shape[-1]     # > Cin when the input was zero-padded to 16 channels (first layer)
+            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(0, Cx, Cout):
+                return ops.tc_conv3d_fwd(x, ops.tc_pack(w, Cx, Cout, 27, Cin * 27, False, cin_valid=Cin), bias, out)
+            assert Cx == Cin
             wp = ops.conv_pack(w, Cin, Cout, 27, Cin * 27, False)
         else:            # ConvTranspose3d weight [Cin, Cout, 27]
             Cin, Cout = w.shape[0], w.shape[1]
@@ -114,8 +116,14 @@ class Engine:
     def _conv_wgrad(self, x, dy, dw, mode=0):
         if mode == 0:    # dw [Cout, Cin, 27]
             Cout, Cin = dw.shape[0], dw.shape[1]
-            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_wgrad_supported(0, Cin, Cout):
-                return ops.tc_conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
+            Cx = x.shape[-1]
+            if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_wgrad_supported(0, Cx, Cout):
+                if Cx == Cin:
+                    return ops.tc_conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
+                tmp = torch.empty((Cout, Cx * 27), dtype=torch.float32, device=dw.device)   # zero-padded input channels
+                ops.tc_conv3d_wgrad(x, dy, tmp, 27, Cx * 27, 0)
+                return ops.add_rows_f32(dw.view(Cout, Cin * 27), tmp[:, :Cin * 27], False)
+            assert Cx == Cin
             ops.conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
         else:            # dw [Cin, Cout, 27]
             Cin, Cout = dw.shape[0], dw.shape[1]
@@ -344,7 +352,8 @@ class Engine:
         at3 = upconv("up3", at2)
 
         # ---------------- encoder; skip tensors are written straight into the decoder concat buffers
-        xcl = ops.ncdhw_to_cl(x, dtype)
+        pad = 16 if (self.use_tc and dtype == torch.bfloat16 and M < 16 and ops.tc_supported(0, 16, nf)) else 0
+        xcl = ops.ncdhw_to_cl(x, dtype, pad_to=pad)
         c.xcl = xcl
         cat1 = empty((B, D, H, W, 2 * nf))
         cat2 = empty((B, D // 2, H // 2, W // 2, 4 * nf))

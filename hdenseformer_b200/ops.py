@@ -86,10 +86,12 @@ def tc_supported(mode: int, Cin: int, Cout: int) -> bool:
     return bool(_lib().hdf_tc_supported(mode, Cin, Cout))
 
 
-def tc_pack(w: torch.Tensor, Cin: int, Cout: int, stride_ci: int, stride_co: int, flip: bool) -> torch.Tensor:
-    """packed[tap][co][ci] bf16 = w[ci*stride_ci + co*stride_co + (26-tap if flip else tap)]"""
+def tc_pack(w: torch.Tensor, Cin: int, Cout: int, stride_ci: int, stride_co: int, flip: bool,
+            cin_valid: Optional[int] = None) -> torch.Tensor:
+    """packed[tap][co][ci] bf16 = w[ci*stride_ci + co*stride_co + (26-tap if flip else tap)], zero for ci >= cin_valid"""
     out = torch.empty((27, Cout, Cin), dtype=torch.bfloat16, device=w.device)
-    _C.check(_lib().hdf_tc_pack_weights(_p(w), _p(out), Cin, Cout, stride_ci, stride_co, int(flip), _s()), "tc_pack")
+    _C.check(_lib().hdf_tc_pack_weights(_p(w), _p(out), Cin, Cout, stride_ci, stride_co, int(flip),
+                                        Cin if cin_valid is None else cin_valid, _s()), "tc_pack")
     return out
 
 
@@ -206,11 +208,14 @@ def upsample2_bwd(dout: torch.Tensor, dx: torch.Tensor, accumulate: bool = False
     return dx
 
 
-def ncdhw_to_cl(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+def ncdhw_to_cl(x: torch.Tensor, dtype: torch.dtype, pad_to: int = 0) -> torch.Tensor:
+    """NCDHW fp32 -> channels-last `dtype`; with pad_to > C the extra channels are zero."""
     N, Cc = x.shape[0], x.shape[1]
-    out = torch.empty((N, *x.shape[2:], Cc), dtype=dtype, device=x.device)
+    Cp = max(Cc, pad_to)
+    alloc = torch.zeros if Cp > Cc else torch.empty
+    out = alloc((N, *x.shape[2:], Cp), dtype=dtype, device=x.device)
     V = x.numel() // (N * Cc)
-    _C.check(_lib().hdf_ncdhw_to_cl(_DT[dtype], _p(x), _p(out), Cc, N, Cc, V, _s()), "ncdhw_to_cl")
+    _C.check(_lib().hdf_ncdhw_to_cl(_DT[dtype], _p(x), _p(out), Cp, N, Cc, V, _s()), "ncdhw_to_cl")
     return out
 
 

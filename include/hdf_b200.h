@@ -51,7 +51,8 @@ int hdf_conv3d_wgrad(int dtype, int mode, const void* x, long long ldx, const vo
 int hdf_tc_supported(int mode, int Cin, int Cout);
 size_t hdf_tc_pack_bytes(int Cin, int Cout);
 int hdf_tc_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, long long stride_ci, long long stride_co,
-                        int flip, void* stream); /* packed[tap][co][ci] bf16 (K-major B operand per tap) */
+                        int flip, int cin_valid, void* stream); /* packed[tap][co][ci] bf16 (K-major B operand per tap);
+                        channels ci >= cin_valid are zero (K padding for 2..4-channel inputs) */
 int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y,
                       long long ldy, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* stream);
 int hdf_tc_wgrad_supported(int mode, int Cin, int Cout);   /* mode 0 or 1 */

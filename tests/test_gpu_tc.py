@@ -148,3 +148,27 @@ def test_tc_conv_transpose_fwd_dgrad_wgrad(cin, cout, size, N):
         ops.tc_conv3d_wgrad(x, g, dw, cout * 27, 27, 1)
         err = ((dw - wq.grad).abs().max() / wq.grad.abs().max()).item()
         assert err < 1e-3, err
+
+
+def test_tc_first_layer_zero_padded_channels():
+    """2-channel input zero-padded to 16 channels so the first conv and its weight gradient run on tensor cores."""
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    torch.manual_seed(3)
+    x = torch.randn(2, 2, 16, 16, 16, device=DEV)
+    w = torch.randn(32, 2, 3, 3, 3, device=DEV) / math.sqrt(54)
+    xcl = ops.ncdhw_to_cl(x, torch.bfloat16, pad_to=16)
+    assert xcl.shape[-1] == 16 and xcl[..., 2:].abs().max().item() == 0
+    y = torch.empty(2, 16, 16, 16, 32, dtype=torch.bfloat16, device=DEV)
+    ops.tc_conv3d_fwd(xcl, ops.tc_pack(w, 16, 32, 27, 2 * 27, False, cin_valid=2), None, y)
+    xq = xcl[..., :2].float().permute(0, 4, 1, 2, 3)
+    wq = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv3d(xq, wq, None, padding=1)
+    refl = ref.detach().permute(0, 2, 3, 4, 1)
+    assert ((y.float() - refl).abs().max() / refl.abs().max()).item() < 1e-2
+    g = torch.randn(2, 16, 16, 16, 32, device=DEV).to(torch.bfloat16)
+    ref.backward(g.float().permute(0, 4, 1, 2, 3))
+    tmp = torch.empty(32, 16 * 27, device=DEV)
+    ops.tc_conv3d_wgrad(xcl, g, tmp, 27, 16 * 27, 0)
+    dw = tmp[:, :54].reshape(32, 2, 3, 3, 3)
+    assert ((dw - wq.grad).abs().max() / wq.grad.abs().max()).item() < 1e-3
+    assert tmp[:, 54:].abs().max().item() == 0
