@@ -133,11 +133,17 @@ struct TcConvParams {
   int Do, Ho, Wo;              // output tensor dims
   int in_scale, out_scale;
   TcTaps taps;
-  int TD, TH, TW;
+  int TD, TH, TW;              // TMA box (TW is the box width, including the 2 halo columns in fold mode)
+  int TWstep;                  // tile origin step along W (= TW, or TW-2 in fold mode)
   int nTd, nTh, nTw;
   int num_tiles;
   int KC, kchunks, stages;
-  uint32_t a_bytes, b_bytes, stage_bytes;  // stage_bytes = round1024(a) + round1024(b)
+  int fold;                    // 1: the three kw taps are folded into the MMA N dimension (N = 3*Cout) and
+                               //    recombined across TMEM lanes (rows) in the epilogue with warp shuffles
+  int Nmma;                    // MMA N = accumulator columns (Cout, or 3*Cout when folded)
+  int b_resident;              // 1: all weight tiles stay resident in shared memory for the whole kernel
+  uint32_t b_region;           // round1024(b_bytes)
+  uint32_t a_bytes, b_bytes, stage_bytes;  // stage_bytes = round1024(a) (+ round1024(b) when B is streamed)
   uint32_t layout, sbo;                    // UMMA layout type / stride-byte-offset of the swizzle mode
   uint32_t tmem_cols;
   long long ldy;
@@ -153,13 +159,17 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t a_region = (p.a_bytes + 1023u) & ~1023u;
-  // barrier block lives after the stage ring
-  const uint32_t bar_base = smem_base + p.stages * p.stage_bytes;
+  const int ntaps_total = p.taps.first[p.taps.ncls];
+  // smem: [resident weight tiles] [stage ring] [barriers]
+  const uint32_t bres_base = smem_base;
+  const uint32_t ring_base = smem_base + (p.b_resident ? (uint32_t)(ntaps_total * p.kchunks) * p.b_region : 0u);
+  const uint32_t bar_base = ring_base + p.stages * p.stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  const uint32_t bres_bar = bar_base + 8u * (2 * p.stages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 5);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -170,6 +180,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -184,6 +195,13 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      if (p.b_resident) {
+        mbar_expect_tx(bres_bar, (uint32_t)(ntaps_total * p.kchunks) * p.b_bytes);
+        for (int e = 0; e < ntaps_total; ++e)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_2d(bres_base + (uint32_t)(e * p.kchunks + kc) * p.b_region, &tmw, bres_bar, kc * p.KC,
+                        (int)p.taps.widx[e] * p.Cout);
+      }
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int cls = tile / tiles_per_cls;
@@ -193,16 +211,16 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         const int tw = r % p.nTw; r /= p.nTw;
         const int th = r % p.nTh;
         const int td = r / p.nTh;
-        const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TW * p.in_scale;
+        const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TWstep * p.in_scale;
         const int e0 = p.taps.first[cls];
         const int kiters = (p.taps.first[cls + 1] - e0) * p.kchunks;
         for (int it = 0; it < kiters; ++it) {
           const int e = e0 + it / p.kchunks, kc = it % p.kchunks;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), p.a_bytes + p.b_bytes);
-          const uint32_t a_dst = smem_base + s * p.stage_bytes;
+          mbar_expect_tx(full_bar(s), p.a_bytes + (p.b_resident ? 0u : p.b_bytes));
+          const uint32_t a_dst = ring_base + s * p.stage_bytes;
           tma_load_5d(a_dst, &tmx, full_bar(s), kc * p.KC, w0 + p.taps.dw[e], h0 + p.taps.dh[e], d0 + p.taps.dd[e], n);
-          tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, (int)p.taps.widx[e] * p.Cout);
+          if (!p.b_resident) tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, (int)p.taps.widx[e] * p.Cout);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -210,21 +228,24 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc(128, p.Cout, 0, 0);
+      const uint32_t idesc = umma_idesc(128, p.Nmma, 0, 0);
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t accph = 0;
+      if (p.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int cls = tile / tiles_per_cls;
-        const int kiters = (p.taps.first[cls + 1] - p.taps.first[cls]) * p.kchunks;
+        const int e0 = p.taps.first[cls];
+        const int kiters = (p.taps.first[cls + 1] - e0) * p.kchunks;
         mbar_wait(tempty_bar(acc), accph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Nmma);
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + s * p.stage_bytes;
+          const uint32_t a_addr = ring_base + s * p.stage_bytes;
+          const uint32_t b_addr = p.b_resident ? bres_base + (uint32_t)(e0 * p.kchunks + it) * p.b_region : a_addr + a_region;
           const uint64_t adesc = umma_desc(a_addr, 16, p.sbo, p.layout);
-          const uint64_t bdesc = umma_desc(a_addr + a_region, 16, p.sbo, p.layout);
+          const uint64_t bdesc = umma_desc(b_addr, 16, p.sbo, p.layout);
           const int ksteps = p.KC / 16;
           for (int k = 0; k < ksteps; ++k)  // +32 B per K=16 step inside the swizzled row (encoded >>4)
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
@@ -249,24 +270,48 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       const int tw = r % p.nTw; r /= p.nTw;
       const int th = r % p.nTh;
       const int td = r / p.nTh;
-      const int d = td * p.TD + md, h = th * p.TH + mh, w = tw * p.TW + mw;
-      const bool valid = d < p.D && h < p.H && w < p.W;
+      const int d = td * p.TD + md, h = th * p.TH + mh, w = tw * p.TWstep + mw;
+      const bool valid = d < p.D && h < p.H && w < p.W && mw < p.TWstep;
       const int od = d * p.out_scale + p.taps.pd[cls], oh = h * p.out_scale + p.taps.ph[cls],
                 ow = w * p.out_scale + p.taps.pw[cls];
       bf16* yrow = p.y + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.ldy;
       mbar_wait(tfull_bar(acc), accph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout);
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (valid) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Nmma);
+      if (!p.fold) {
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[c0 + j] : 0.f);
+            store8<bf16>(yrow + c0, f);
+            store8<bf16>(yrow + c0 + 8, f + 8);
+          }
+        }
+      } else {
+        // row m holds, for kw = 0,1,2, the partial sums P_kw[m] = sum_{kd,kh,ci} X[box row m] * W[kd,kh,kw];
+        // output column mw needs P_0[m] + P_1[m+1] + P_2[m+2]  (box row m+kw = input w0-1+mw+kw): the rows are
+        // neighbouring TMEM lanes of the same warp (a box line never straddles a warp), fetched with shuffles.
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld16(taddr + (uint32_t)c0, v0);
+          tmem_ld16(taddr + (uint32_t)(p.Cout + c0), v1);
+          tmem_ld16(taddr + (uint32_t)(2 * p.Cout + c0), v2);
+          tmem_ld_wait();
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[c0 + j] : 0.f);
-          store8<bf16>(yrow + c0, f);
-          store8<bf16>(yrow + c0 + 8, f + 8);
+          for (int j = 0; j < 16; ++j) {
+            const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);
+            const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 2);
+            f[j] = __uint_as_float(v0[j]) + a1 + a2 + (p.bias ? p.bias[c0 + j] : 0.f);
+          }
+          if (valid) {
+            store8<bf16>(yrow + c0, f);
+            store8<bf16>(yrow + c0 + 8, f + 8);
+          }
         }
       }
       tc_fence_before();
@@ -485,6 +530,18 @@ void pick_tile(int D, int H, int W, int& TD, int& TH, int& TW) {
     }
 }
 
+// fold mode (mode 0 only): 9 (kd,kh) entries; the box starts one column left (dw = -1) and the weight tile of
+// an entry is the 3*Cout rows of taps (kd,kh,0..2), which are consecutive in the packed [27][Cout][Cin] layout
+void build_taps_fold(TcTaps& t) {
+  memset(&t, 0, sizeof(t));
+  t.ncls = 1;
+  t.first[0] = 0; t.first[1] = 9;
+  for (int e = 0; e < 9; ++e) {
+    t.dd[e] = (signed char)(e / 3 - 1); t.dh[e] = (signed char)(e % 3 - 1); t.dw[e] = -1;
+    t.widx[e] = (signed char)(e * 3);
+  }
+}
+
 void build_taps(int mode, TcTaps& t) {
   memset(&t, 0, sizeof(t));
   if (mode == 0 || mode == 2) {
@@ -575,23 +632,57 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
   p.Do = Do; p.Ho = Ho; p.Wo = Wo;
   p.in_scale = mode == 2 ? 2 : 1;
   p.out_scale = mode == 1 ? 2 : 1;
-  build_taps(mode, p.taps);
-  pick_tile(D, H, W, p.TD, p.TH, p.TW);
-  p.nTd = cdiv(D, p.TD); p.nTh = cdiv(H, p.TH); p.nTw = cdiv(W, p.TW);
-  p.num_tiles = p.taps.ncls * N * p.nTd * p.nTh * p.nTw;
   p.KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0) ? 32 : 16;
   p.kchunks = Cin / p.KC;
   p.a_bytes = 128u * p.KC * 2u;
-  p.b_bytes = (uint32_t)Cout * p.KC * 2u;
-  p.stage_bytes = ((p.a_bytes + 1023u) & ~1023u) + ((p.b_bytes + 1023u) & ~1023u);
   const int inner = p.KC * 2;
   p.layout = inner == 128 ? 2u : inner == 64 ? 4u : 6u;
   p.sbo = 8u * inner;
-  p.stages = (int)(196608u / p.stage_bytes);
+
+  // ---- plain plan: one TMA box + one MMA group per tap
+  build_taps(mode, p.taps);
+  pick_tile(D, H, W, p.TD, p.TH, p.TW);
+  p.TWstep = p.TW;
+  p.nTd = cdiv(D, p.TD); p.nTh = cdiv(H, p.TH); p.nTw = cdiv(W, p.TW);
+  p.fold = 0;
+  p.Nmma = Cout;
+  double best_cost = (double)p.nTd * p.nTh * p.nTw * 27.0 * (128.0 + Cout);   // ~ L2->SMEM rows per sample
+  // ---- folded plan (stride-1 conv, 3*Cout <= 256): box width 32 or 16 incl. 2 halo columns, 9 boxes per tile
+  static const char* no_fold = getenv("HDF_TC_NO_FOLD");
+  if (mode == 0 && 3 * Cout <= 256 && !no_fold) {
+    for (int wb = 32; wb >= 16; wb /= 2) {
+      const int lines = 128 / wb, step = wb - 2;
+      int bth = 1, btd = lines; long long bt = -1;
+      for (int th = 1; th <= lines; th *= 2) {
+        const int td = lines / th;
+        const long long t = (long long)cdiv(D, td) * cdiv(H, th);
+        if (bt < 0 || t < bt) { bt = t; bth = th; btd = td; }
+      }
+      const double cost = (double)bt * cdiv(W, step) * 9.0 * 128.0;
+      if (cost < best_cost) {
+        best_cost = cost;
+        p.fold = 1; p.TW = wb; p.TWstep = step; p.TH = bth; p.TD = btd;
+        p.nTd = cdiv(D, btd); p.nTh = cdiv(H, bth); p.nTw = cdiv(W, step);
+        p.Nmma = 3 * Cout;
+      }
+    }
+    if (p.fold) build_taps_fold(p.taps);
+  }
+  p.num_tiles = p.taps.ncls * N * p.nTd * p.nTh * p.nTw;
+  p.b_bytes = (uint32_t)p.Nmma * p.KC * 2u;
+  p.b_region = (p.b_bytes + 1023u) & ~1023u;
+  const int ntaps_total = p.taps.first[p.taps.ncls];
+  const size_t bres_bytes = (size_t)ntaps_total * p.kchunks * p.b_region;
+  static const char* no_res = getenv("HDF_TC_NO_RESIDENT");
+  p.b_resident = (bres_bytes <= 114 * 1024 && !no_res) ? 1 : 0;
+  const uint32_t a_region_h = (p.a_bytes + 1023u) & ~1023u;
+  p.stage_bytes = a_region_h + (p.b_resident ? 0u : p.b_region);
+  const size_t ring_budget = 200 * 1024 - (p.b_resident ? bres_bytes : 0);
+  p.stages = (int)(ring_budget / p.stage_bytes);
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) { hdf_set_error("hdf_tc_conv3d_fwd: stage too large"); return HDF_ERR_UNSUPPORTED; }
   uint32_t cols = 32;
-  while (cols < 2u * Cout) cols *= 2;
+  while (cols < 2u * p.Nmma) cols *= 2;
   p.tmem_cols = cols;
   p.ldy = ldy; p.bias = bias; p.y = (bf16*)y;
 
@@ -611,14 +702,15 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
   {
     cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
     cuuint64_t gstr[1] = {(cuuint64_t)Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)Cout};
+    cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)p.Nmma};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tmw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed_bf16), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(inner), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { hdf_set_error("hdf_tc_conv3d_fwd: encode(w) failed: %d", (int)r); return HDF_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ + 8 * (2 * p.stages + 4) + 16;
+  const size_t smem = (p.b_resident ? bres_bytes : 0) + (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ +
+                      8 * (2 * p.stages + 6) + 16;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
