@@ -105,16 +105,20 @@ struct ColSumF {
   }
 };
 
+// one warp per (n, c): lanes stride over the chunk partials, fixed-order shuffle reduction (deterministic)
 __global__ void stats_finalize_kernel(const double* __restrict__ partial, int chunks, int C, long long V, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd, int NC) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (i >= NC) return;
   const int n = i / C, c = i % C;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < chunks; ++k) {
+  for (int k = lane; k < chunks; k += 32) {
     s += partial[(((long long)n * chunks + k) * 2 + 0) * C + c];
     q += partial[(((long long)n * chunks + k) * 2 + 1) * C + c];
   }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane != 0) return;
   const double m = s / (double)V;
   double var = q / (double)V - m * m;
   if (var < 0.0) var = 0.0;
@@ -124,24 +128,29 @@ __global__ void stats_finalize_kernel(const double* __restrict__ partial, int ch
 
 __global__ void sums_finalize_kernel(const double* __restrict__ partial, int chunks, int C, float* __restrict__ s1,
                                      float* __restrict__ s2, int NC) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (i >= NC) return;
   const int n = i / C, c = i % C;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < chunks; ++k) {
+  for (int k = lane; k < chunks; k += 32) {
     s += partial[(((long long)n * chunks + k) * 2 + 0) * C + c];
     q += partial[(((long long)n * chunks + k) * 2 + 1) * C + c];
   }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane != 0) return;
   s1[i] = (float)s;
   if (s2) s2[i] = (float)q;
 }
 
 __global__ void colsum_finalize_kernel(const double* __restrict__ partial, int chunks, int C, float* __restrict__ out,
                                        int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (c >= C) return;
   double s = 0.0;
-  for (int k = 0; k < chunks; ++k) s += partial[((long long)k * 2 + 0) * C + c];
+  for (int k = lane; k < chunks; k += 32) s += partial[((long long)k * 2 + 0) * C + c];
+  s = warp_sum_d(s);
+  if (lane != 0) return;
   out[c] = accumulate ? out[c] + (float)s : (float)s;
 }
 
@@ -519,60 +528,61 @@ __global__ void head_dgrad_kernel(const T* __restrict__ g, const float* __restri
   }
 }
 
-// partial[chunk][k][C+1]: dW[k][c] = sum_v g[k][v] a[v][c];  column C holds db[k]
-template <typename T>
+// partial[chunk][k][C+1]: dW[k][c] = sum_v g[k][v] a[v][c];  column C holds db[k].
+// Thread = (row lane, VEC-channel group): 128-bit loads of the activation row, coalesced loads of g.
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ a, long long lda,
                                                         long long V, int C, int ncls, long long total, int rows_per_chunk,
                                                         float* __restrict__ partial) {
-  extern __shared__ float sm[];  // [lanes][ncls][C]
+  extern __shared__ float sm[];  // [lanes][ncls][C] then [lanes][ncls]
   const int tid = threadIdx.x;
-  const int cb = min(C, 256);
-  const int lanes = 256 / cb;
-  const int lane = tid / cb;
+  const int cpv = C / VEC;                 // channel groups per row (<= 256 guaranteed by host)
+  const int lanes = 256 / cpv;
+  const int lane = tid / cpv, cg = tid % cpv;
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
   const long long r1 = min(total, r0 + rows_per_chunk);
-  for (int cbase = 0; cbase < C; cbase += cb) {
-    const int c = cbase + tid % cb;
-    float acc[MAXCLS], accb[MAXCLS];
+  float acc[MAXCLS][VEC], accb[MAXCLS];
 #pragma unroll
-    for (int k = 0; k < MAXCLS; ++k) acc[k] = accb[k] = 0.f;
-    if (lane < lanes && c < C) {
-      for (long long row = r0 + lane; row < r1; row += lanes) {
-        const long long n = row / V, v = row % V;
-        const float x = to_f(a[row * lda + c]);
+  for (int k = 0; k < MAXCLS; ++k) {
+    accb[k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < MAXCLS; ++k) {
-          if (k < ncls) {
-            const float gv = to_f(g[(n * ncls + k) * V + v]);
-            acc[k] = fmaf(gv, x, acc[k]);
-            accb[k] += gv;
-          }
+    for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
+  }
+  if (lane < lanes) {
+    for (long long row = r0 + lane; row < r1; row += lanes) {
+      const long long n = row / V, v = row % V;
+      float x[VEC];
+      loadv<T, VEC>(a + row * lda + cg * VEC, x);
+#pragma unroll
+      for (int k = 0; k < MAXCLS; ++k) {
+        if (k < ncls) {
+          const float gv = to_f(g[(n * ncls + k) * V + v]);
+          accb[k] += gv;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(gv, x[j], acc[k][j]);
         }
       }
     }
-    if (lane < lanes && c < C)
-      for (int k = 0; k < ncls; ++k) sm[(lane * ncls + k) * cb + (c - cbase)] = acc[k];
-    __syncthreads();
-    for (int i = tid; i < ncls * cb; i += 256) {
-      const int k = i / cb, cc = i % cb;
-      if (cbase + cc < C) {
-        float s = 0.f;
-        for (int l = 0; l < lanes; ++l) s += sm[(l * ncls + k) * cb + cc];
-        partial[((long long)blockIdx.x * ncls + k) * (C + 1) + cbase + cc] = s;
+#pragma unroll
+    for (int k = 0; k < MAXCLS; ++k) {
+      if (k < ncls) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sm[(lane * ncls + k) * C + cg * VEC + j] = acc[k][j];
+        if (cg == 0) sm[lanes * ncls * C + lane * ncls + k] = accb[k];
       }
     }
-    __syncthreads();
-    if (cbase == 0) {  // bias: lanes of channel 0 hold complete sums over their rows
-      if (lane < lanes && tid % cb == 0)
-        for (int k = 0; k < ncls; ++k) sm[lane * ncls + k] = accb[k];
-      __syncthreads();
-      if (tid < ncls) {
-        float s = 0.f;
-        for (int l = 0; l < lanes; ++l) s += sm[l * ncls + tid];
-        partial[((long long)blockIdx.x * ncls + tid) * (C + 1) + C] = s;
-      }
-      __syncthreads();
-    }
+  }
+  __syncthreads();
+  for (int i = tid; i < ncls * C; i += 256) {
+    float s2 = 0.f;
+    for (int l = 0; l < lanes; ++l) s2 += sm[l * ncls * C + i];
+    const int k = i / C, c = i % C;
+    partial[((long long)blockIdx.x * ncls + k) * (C + 1) + c] = s2;
+  }
+  if (tid < ncls) {
+    float s2 = 0.f;
+    for (int l = 0; l < lanes; ++l) s2 += sm[lanes * ncls * C + l * ncls + tid];
+    partial[((long long)blockIdx.x * ncls + tid) * (C + 1) + C] = s2;
   }
 }
 
@@ -624,7 +634,7 @@ int hdf_instnorm_stats(int dtype, const void* y, long long ldy, int N, long long
     int rc = launch_rowreduce<T>(f, y, ldy, nullptr, 0, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_stats");
     if (rc) return rc;
   });
-  stats_finalize_kernel<<<cdiv(N * C, 128), 128, 0, s>>>((const double*)workspace, chunks, C, V, eps, mean, rstd, N * C);
+  stats_finalize_kernel<<<cdiv((long long)N * C * 32, 128), 128, 0, s>>>((const double*)workspace, chunks, C, V, eps, mean, rstd, N * C);
   HDF_LAUNCH_CHECK("hdf_instnorm_stats/finalize");
   return HDF_OK;
 }
@@ -657,7 +667,7 @@ int hdf_instnorm_bwd(int dtype, const void* dout, long long ldd, const void* y, 
     int rc = launch_rowreduce<T>(f, dout, ldd, y, ldy, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_bwd/reduce");
     if (rc) return rc;
   });
-  sums_finalize_kernel<<<cdiv(N * C, 128), 128, 0, s>>>((const double*)workspace, chunks, C, s1, s2, N * C);
+  sums_finalize_kernel<<<cdiv((long long)N * C * 32, 128), 128, 0, s>>>((const double*)workspace, chunks, C, s1, s2, N * C);
   HDF_LAUNCH_CHECK("hdf_instnorm_bwd/finalize");
   if (dgamma || dbeta) {
     in_param_grads_kernel<<<cdiv(C, 128), 128, 0, s>>>(s1, s2, N, C, dgamma, dbeta, accumulate_params);
@@ -683,7 +693,7 @@ int hdf_colsum(int dtype, const void* x, long long ld, long long rows, int C, fl
     int rc = launch_rowreduce<T>(f, x, ld, nullptr, 0, 1, rows, C, (double*)workspace, chunks, s, "hdf_colsum");
     if (rc) return rc;
   });
-  colsum_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>((const double*)workspace, chunks, C, out, accumulate);
+  colsum_finalize_kernel<<<cdiv((long long)C * 32, 128), 128, 0, s>>>((const double*)workspace, chunks, C, out, accumulate);
   HDF_LAUNCH_CHECK("hdf_colsum/finalize");
   return HDF_OK;
 }
@@ -814,9 +824,16 @@ int hdf_head_bwd(int dtype, const void* g, const void* a, long long lda, const f
   const int rpc = cdiv(total, chunks);
   chunks = cdiv(total, rpc);
   HDF_DISPATCH_DTYPE(dtype, T, {
-    const int cb = C < 256 ? C : 256;
-    const size_t smem = (size_t)(256 / cb) * ncls * cb * sizeof(float) + 64;
-    head_wgrad_kernel<T><<<chunks, 256, smem, s>>>((const T*)g, (const T*)a, lda, V, C, ncls, total, rpc, (float*)workspace);
+    {
+      const bool vecw = can_vec<T>(a, lda, C);
+      HDF_REQUIRE(vecw ? (C / VecOf<T>::value <= 256) : (C <= 256), "hdf_head_bwd: C=%d too large", C);
+      HDF_VEC_DISPATCH(vecw, {
+        const int lanes = 256 / (C / VEC);
+        const size_t smem = (size_t)lanes * ncls * (C + 1) * sizeof(float);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(head_wgrad_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        head_wgrad_kernel<T, VEC><<<chunks, 256, smem, s>>>((const T*)g, (const T*)a, lda, V, C, ncls, total, rpc, (float*)workspace);
+      });
+    }
     HDF_LAUNCH_CHECK("hdf_head_bwd/wgrad");
     head_wgrad_finalize_kernel<<<cdiv(ncls * (C + 1), 128), 128, 0, s>>>((const float*)workspace, chunks, C, ncls, dw, db, accumulate_params);
     HDF_LAUNCH_CHECK("hdf_head_bwd/finalize");

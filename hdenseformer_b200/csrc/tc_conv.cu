@@ -142,6 +142,12 @@ struct TcConvParams {
                                //    recombined across TMEM lanes (rows) in the epilogue with warp shuffles
   int Nmma;                    // MMA N = accumulator columns (Cout, or 3*Cout when folded)
   int b_resident;              // 1: all weight tiles stay resident in shared memory for the whole kernel
+  int a_cpasync;               // 1: the input box is gathered by 4 producer warps with 16-byte cp.async (zero-filled
+                               //    out of bounds) instead of TMA: the TMA unit retires ~1 box row per 5.5 clk, which
+                               //    caps 64/128-byte rows well below L2 bandwidth (profiles/r1_ncu_conv_fwd_tma.txt)
+  const bf16* x;               // input tensor (cp.async path)
+  long long ldx;
+  int Di, Hi, Wi;              // input tensor dims
   uint32_t b_region;           // round1024(b_bytes)
   uint32_t a_bytes, b_bytes, stage_bytes;  // stage_bytes = round1024(a) (+ round1024(b) when B is streamed)
   uint32_t layout, sbo;                    // UMMA layout type / stride-byte-offset of the swizzle mode
@@ -151,9 +157,21 @@ struct TcConvParams {
   bf16* y;
 };
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 256;     // wgrad kernel: warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 epilogue
+constexpr int FWD_THREADS = 288;    // fwd kernel: warps 0-3 producers, 4 MMA + TMEM alloc, 5-8 epilogue
+constexpr int CP_LAG = 3;           // cp.async groups kept in flight per producer thread
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -178,12 +196,15 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     tma_prefetch_desc(&tmw);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // full barrier arrivals per phase: TMA path = 1 (expect_tx); cp.async path = 128 producer threads
+    // (+1 expect_tx arrival when the weight tile is streamed by TMA into the same stage)
+    const uint32_t full_count = p.a_cpasync ? (128u + (p.b_resident ? 0u : 1u)) : 1u;
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 4) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -192,15 +213,59 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   const int tiles_per_n = p.nTd * p.nTh * p.nTw;
   const int tiles_per_cls = p.N * tiles_per_n;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      if (p.b_resident) {
-        mbar_expect_tx(bres_bar, (uint32_t)(ntaps_total * p.kchunks) * p.b_bytes);
-        for (int e = 0; e < ntaps_total; ++e)
-          for (int kc = 0; kc < p.kchunks; ++kc)
-            tma_load_2d(bres_base + (uint32_t)(e * p.kchunks + kc) * p.b_region, &tmw, bres_bar, kc * p.KC,
-                        (int)p.taps.widx[e] * p.Cout);
+  if (warp < 4) {
+    // ===== producers =====
+    const int ptid = threadIdx.x;   // 0..127
+    if (ptid == 0 && p.b_resident) {
+      mbar_expect_tx(bres_bar, (uint32_t)(ntaps_total * p.kchunks) * p.b_bytes);
+      for (int e = 0; e < ntaps_total; ++e)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d(bres_base + (uint32_t)(e * p.kchunks + kc) * p.b_region, &tmw, bres_bar, kc * p.KC,
+                      (int)p.taps.widx[e] * p.Cout);
+    }
+    if (!p.a_cpasync) {
+      if (ptid == 0) {
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          const int cls = tile / tiles_per_cls;
+          int r = tile - cls * tiles_per_cls;
+          const int n = r / tiles_per_n;
+          r -= n * tiles_per_n;
+          const int tw = r % p.nTw; r /= p.nTw;
+          const int th = r % p.nTh;
+          const int td = r / p.nTh;
+          const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TWstep * p.in_scale;
+          const int e0 = p.taps.first[cls];
+          const int kiters = (p.taps.first[cls + 1] - e0) * p.kchunks;
+          for (int it = 0; it < kiters; ++it) {
+            const int e = e0 + it / p.kchunks, kc = it % p.kchunks;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            mbar_expect_tx(full_bar(s), p.a_bytes + (p.b_resident ? 0u : p.b_bytes));
+            const uint32_t a_dst = ring_base + s * p.stage_bytes;
+            tma_load_5d(a_dst, &tmx, full_bar(s), kc * p.KC, w0 + p.taps.dw[e], h0 + p.taps.dh[e], d0 + p.taps.dd[e], n);
+            if (!p.b_resident) tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, (int)p.taps.widx[e] * p.Cout);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    } else {
+      // ---- cp.async gather: thread -> (16-byte chunk j of the row, rows rsub + i*rpp), written with the same
+      // XOR swizzle the UMMA descriptor expects (address bits [4,7) ^= bits [7,10) within the swizzle span)
+      const int cpr = p.KC / 8;          // 16-byte chunks per row: 2, 4 or 8
+      const int rpp = 128 / cpr;         // rows covered by one pass of the 128 producer threads
+      const int j = ptid % cpr, rsub = ptid / cpr;
+      const uint32_t rowbytes = (uint32_t)p.KC * 2u;
+      int rcol[8], rlh[8], rld[8];
+      uint32_t roff[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + i * rpp;
+        rcol[i] = (r % p.TW) * p.in_scale;
+        const int line = r / p.TW;
+        rlh[i] = (line % p.TH) * p.in_scale;
+        rld[i] = (line / p.TH) * p.in_scale;
+        const uint32_t phys = (uint32_t)j ^ (((uint32_t)r * rowbytes >> 7) & (uint32_t)(cpr - 1));
+        roff[i] = (uint32_t)r * rowbytes + phys * 16u;
       }
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -214,18 +279,35 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TWstep * p.in_scale;
         const int e0 = p.taps.first[cls];
         const int kiters = (p.taps.first[cls + 1] - e0) * p.kchunks;
+        const bf16* xn = p.x + (long long)n * p.Di * p.Hi * p.Wi * p.ldx + j * 8;
         for (int it = 0; it < kiters; ++it) {
           const int e = e0 + it / p.kchunks, kc = it % p.kchunks;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), p.a_bytes + (p.b_resident ? 0u : p.b_bytes));
           const uint32_t a_dst = ring_base + s * p.stage_bytes;
-          tma_load_5d(a_dst, &tmx, full_bar(s), kc * p.KC, w0 + p.taps.dw[e], h0 + p.taps.dh[e], d0 + p.taps.dd[e], n);
-          if (!p.b_resident) tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, (int)p.taps.widx[e] * p.Cout);
+          if (ptid == 0 && !p.b_resident) {
+            mbar_expect_tx(full_bar(s), p.b_bytes);
+            tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, (int)p.taps.widx[e] * p.Cout);
+          }
+          const int wo = w0 + p.taps.dw[e], ho = h0 + p.taps.dh[e], dO = d0 + p.taps.dd[e];
+          const bf16* xk = xn + kc * p.KC;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < cpr) {
+              const int w = wo + rcol[i], h = ho + rlh[i], d = dO + rld[i];
+              const bool ok = (unsigned)w < (unsigned)p.Wi && (unsigned)h < (unsigned)p.Hi && (unsigned)d < (unsigned)p.Di;
+              const bf16* src = ok ? xk + (((long long)d * p.Hi + h) * p.Wi + w) * p.ldx : p.x;
+              cp_async16(a_dst + roff[i], src, ok ? 16u : 0u);
+            }
+          }
+          // the barrier receives this thread's arrival when all of its copies above have landed: no thread ever
+          // blocks on its own loads, so up to `stages` boxes (the whole ring) are in flight per SM
+          cp_async_mbar_arrive(full_bar(s));
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
+      cp_async_wait<0>();
     }
-  } else if (warp == 1) {
+  } else if (warp == 4) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = umma_idesc(128, p.Nmma, 0, 0);
@@ -241,6 +323,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Nmma);
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(full_bar(s), ph);
+          if (p.a_cpasync) fence_proxy_async();
           tc_fence_after();
           const uint32_t a_addr = ring_base + s * p.stage_bytes;
           const uint32_t b_addr = p.b_resident ? bres_base + (uint32_t)(e0 * p.kchunks + it) * p.b_region : a_addr + a_region;
@@ -256,9 +339,9 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         if (++acc == 2) { acc = 0; accph ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> (+bias) -> bf16 -> global =====
-    const int q = warp - 4;  // TMEM lane quadrant of this warp
+  } else {
+    // ===== epilogue (warps 5..8): TMEM -> registers -> (+bias) -> bf16 -> global =====
+    const int q = warp % 4;  // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;
     const int mw = m % p.TW, mh = (m / p.TW) % p.TH, md = m / (p.TW * p.TH);
     int acc = 0; uint32_t accph = 0;
@@ -322,7 +405,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -679,12 +762,17 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
   p.stage_bytes = a_region_h + (p.b_resident ? 0u : p.b_region);
   const size_t ring_budget = 200 * 1024 - (p.b_resident ? bres_bytes : 0);
   p.stages = (int)(ring_budget / p.stage_bytes);
-  if (p.stages > 8) p.stages = 8;
+  if (p.stages > 12) p.stages = 12;
   if (p.stages < 2) { hdf_set_error("hdf_tc_conv3d_fwd: stage too large"); return HDF_ERR_UNSUPPORTED; }
   uint32_t cols = 32;
   while (cols < 2u * p.Nmma) cols *= 2;
   p.tmem_cols = cols;
   p.ldy = ldy; p.bias = bias; p.y = (bf16*)y;
+  // measured on B200 (profiles/r1_microbench_conv_v2_cpasync.txt): the cp.async gather is ~2x slower than the
+  // TMA box loads for these shapes, so it stays opt-in for experiments
+  static const char* use_cp = getenv("HDF_TC_CPASYNC");
+  p.a_cpasync = use_cp ? 1 : 0;
+  p.x = (const bf16*)x; p.ldx = ldx; p.Di = Di; p.Hi = Hi; p.Wi = Wi;
 
   CUtensorMap tmx, tmw;
   {
@@ -710,7 +798,7 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
     if (r != CUDA_SUCCESS) { hdf_set_error("hdf_tc_conv3d_fwd: encode(w) failed: %d", (int)r); return HDF_ERR_CUDA; }
   }
   const size_t smem = (p.b_resident ? bres_bytes : 0) + (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ +
-                      8 * (2 * p.stages + 6) + 16;
+                      8 * (2 * p.stages + 6) + 64;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
@@ -718,7 +806,7 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
     configured = 227 * 1024;
   }
   const int grid = p.num_tiles < hdf_sm_count_cached() ? p.num_tiles : hdf_sm_count_cached();
-  tc_conv_fwd_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
+  tc_conv_fwd_kernel<<<grid, FWD_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_fwd");
   return HDF_OK;
 }
