@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--depth", type=int, default=12)
     ap.add_argument("--fp32", action="store_true", help="exact fp32 path instead of bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-kernels", action="store_true", help="extra untimed steps with per-op CUDA events")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
     size = tuple(a.size)
     rank = int(os.environ.get("RANK", 0))
@@ -171,8 +171,9 @@ def main():
     crit = DeepSuperloss(CEPlusDice(weight=None, ignore_index=0))
     decay = [p for n_, p in net.named_parameters() if p.dim() > 1 and not n_.endswith(".bias")]
     no_decay = [p for n_, p in net.named_parameters() if not (p.dim() > 1 and not n_.endswith(".bias"))]
+    use_graph = (world == 1) and not a.no_graph
     opt = torch.optim.Adam([{"params": decay, "weight_decay": 1e-4}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-3,
-                           fused=True)   # grouping of trainer.py:812-819
+                           fused=True, capturable=use_graph)   # grouping of trainer.py:812-819
     dp = T.DataParallelTrainer(net, crit, opt, use_bf16=not a.fp32)
     nb = 2   # two distinct pinned batches, alternated
     host = [(O.synth_petct(a.batch, size, seed=rank * 10 + i).pin_memory(), O.synth_label(a.batch, 2, size, seed=rank * 10 + i).pin_memory())
@@ -198,10 +199,18 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    step_dev = lambda i: dp.step(*devb[i % nb])
+    graphed = None
+    if use_graph:
+        try:
+            graphed = T.GraphedTrainStep(net, crit, opt, devb[0][0], devb[0][1], use_bf16=not a.fp32)
+        except Exception as e:   # keep the benchmark alive; the mode actually used is reported in config.launch
+            print(f"[bench] CUDA-graph capture failed, falling back to eager launches: {e!r}", file=sys.stderr)
+            graphed = None
+    stepper = graphed.step if graphed is not None else dp.step
+    step_dev = lambda i: stepper(*devb[i % nb])
 
     def step_e2e(i):
-        loss = dp.step(*host[i % nb])
+        loss = stepper(*host[i % nb])
         return loss.item()          # D2H read of the step's result
 
     for i in range(warmup):
@@ -209,9 +218,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _C.load().hdf_launch_count()
     ms = timed(step_dev, a.steps)
-    launches = _C.load().hdf_launch_count() - l0
+    # kernels of libhdf_b200 per step: counted on one eager step (a graph replay submits the same kernels in one call)
+    l0 = _C.load().hdf_launch_count()
+    dp.step(*devb[0])
+    torch.cuda.synchronize()
+    launches = (_C.load().hdf_launch_count() - l0) * a.steps
     clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
         step_e2e(i)
@@ -249,7 +261,7 @@ def main():
             "warmup": warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if a.fp32 else "bf16", "data": "synthetic",
             "config": {"workload": workload, "batch_per_gpu": a.batch, "global_batch": a.batch * world,
-                       "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (activations >> 126 MB per step)",
+                       "parallelism": f"dp{world}", "launch": "cuda_graph_replay" if graphed is not None else "eager", "l2": "inputs_exceed_l2 (activations >> 126 MB per step)",
                        "algorithmic_tflop_per_volume": gf_step / 1e3, "achieved_tflops": gf_step * value / 1e3},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_e2e / a.steps,

@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(AT) attn_bwd_dkv_kernel(const float* __restric
 // dz[m,n] = dy[m,n] * dropout_scale(m*N+n) * gelu'(pre[m,n])   (act=1)   or   dy * dropout_scale (act=0)
 __global__ void act_dropout_bwd_kernel(const float* __restrict__ dy, long long ldd, const float* __restrict__ pre,
                                        float* __restrict__ dz, long long ldz, int N, long long total, int act, float p,
-                                       unsigned long long seed, unsigned call_id) {
+                                       const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id) {
+  if (seed_ptr) seed += *seed_ptr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / N;
     const int n = (int)(i % N);
@@ -316,11 +317,11 @@ int hdf_attention_bwd(const float* qkv, long long ld, const float* o, long long 
 }
 
 int hdf_act_dropout_bwd(const float* dy, long long ldd, const float* pre, float* dz, long long ldz, int M, int N, int act,
-                        float p, unsigned long long seed, unsigned call_id, void* stream) {
+                        float p, const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* stream) {
   HDF_REQUIRE(dy && dz && (act == 0 || pre), "hdf_act_dropout_bwd: null pointer");
   const long long total = (long long)M * N;
   act_dropout_bwd_kernel<<<min(2048, cdiv(total, 256)), 256, 0, (cudaStream_t)stream>>>(dy, ldd, pre, dz, ldz, N, total, act,
-                                                                                      p, seed, call_id);
+                                                                                      p, seed_ptr, seed, call_id);
   HDF_LAUNCH_CHECK("hdf_act_dropout_bwd");
   return HDF_OK;
 }

@@ -372,7 +372,8 @@ struct LinearEp {
   float* pre;              // pre-activation (acc + bias) save for backward, [M, N] dense, or null
   int act;                 // 0 none, 1 exact GELU
   float p;                 // dropout prob (0 = off)
-  unsigned long long seed;
+  const unsigned long long* seed_ptr;  // device-resident base seed (CUDA-graph replays advance it) or null
+  unsigned long long seed;             // offset added to *seed_ptr
   unsigned call_id;
   float beta;              // c = beta*c + result   (0 or 1)
   __device__ void store(int, int, int m, int n, const float* acc, int, int N) const {
@@ -382,7 +383,7 @@ struct LinearEp {
       float v = acc[j] + (bias ? bias[n + j] : 0.f);
       if (pre) pre[(long long)m * N + n + j] = v;
       if (act == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-      if (p > 0.f) v *= hdf_dropout_scale(seed, call_id, (unsigned long long)m * N + n + j, p);
+      if (p > 0.f) v *= hdf_dropout_scale(seed + (seed_ptr ? *seed_ptr : 0ull), call_id, (unsigned long long)m * N + n + j, p);
       if (residual) v += residual[(long long)m * ldr + n + j];
       float* q = c + (long long)m * ldc + n + j;
       *q = (beta != 0.f) ? (*q + v) : v;
@@ -465,7 +466,9 @@ __global__ void reduce_transpose_kernel(const float* __restrict__ part, float* _
 
 // tok[m, e] = (tok[m, e] + pos[m % ntok, e]) * dropout
 __global__ void posemb_dropout_kernel(float* __restrict__ tok, long long ld, const float* __restrict__ pos, int ntok, int E,
-                                      long long total, float p, unsigned long long seed, unsigned call_id) {
+                                      long long total, float p, const unsigned long long* seed_ptr,
+                                      unsigned long long seed, unsigned call_id) {
+  if (seed_ptr) seed += *seed_ptr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int e = i % E;
     const long long m = i / E;
@@ -553,7 +556,7 @@ int hdf_conv3d_wgrad(int dtype, int mode, const void* x, long long ldx, const vo
 // img: NCDHW fp32 [B, Mch, D, H, W]; weight [E, 4096] (torch [E,1,16,16,16]); out fp32
 int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, int H, int W, const float* weight,
                         const float* bias, const float* pos, float* out, long long ldo, int E, float p,
-                        unsigned long long seed, unsigned call_id, void* stream) {
+                        const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* stream) {
   HDF_REQUIRE(img && weight && out && (D % 16 == 0) && (H % 16 == 0) && (W % 16 == 0) && (W % 4 == 0),
               "hdf_patch_embed_fwd: bad args (every spatial dim must be a multiple of 16)");
   const int ntok = (D / 16) * (H / 16) * (W / 16);
@@ -561,12 +564,12 @@ int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, i
   PatchA al{img + (long long)modality * D * H * W, (long long)Mch * D * H * W, D, H, W, M, nullptr, false};
   ColMajorB bl{weight, 4096, E};
   // bias + positional embedding: pos is [ntok, E]; fold via residual with row index modulo ntok -> do in two steps:
-  LinearEp ep{out, ldo, bias, nullptr, 0, nullptr, 0, 0.f, seed, call_id, 0.f};
+  LinearEp ep{out, ldo, bias, nullptr, 0, nullptr, 0, 0.f, seed_ptr, seed, call_id, 0.f};
   int rc = launch_gemm(al, bl, ep, M, E, 4096, 1, 1, (cudaStream_t)stream, "hdf_patch_embed_fwd");
   if (rc) return rc;
   const long long total = (long long)M * E;
   posemb_dropout_kernel<<<min(1024, cdiv(total, 256)), 256, 0, (cudaStream_t)stream>>>(out, ldo, pos, ntok, E, total, p,
-                                                                                       seed, call_id);
+                                                                                       seed_ptr, seed, call_id);
   HDF_LAUNCH_CHECK("hdf_patch_embed_fwd/posemb");
   return HDF_OK;
 }
@@ -610,10 +613,11 @@ int hdf_patch_embed_wgrad(const float* img, int B, int Mch, int modality, int D,
 // C[M,N] (ldc) = epilogue(A[M,K] (lda) @ op(B)), op(B) = B^T with B [N,K] (ldb) if b_is_nk else B [K,N] (ldb)
 int hdf_gemm_rowmajor(const float* A, long long lda, const float* Bm, long long ldb, int b_is_nk, float* C, long long ldc,
                       int M, int N, int K, const float* bias, const float* residual, long long ldr, float* pre, int act,
-                      float p, unsigned long long seed, unsigned call_id, int accumulate, void* stream) {
+                      float p, const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, int accumulate,
+                      void* stream) {
   HDF_REQUIRE(A && Bm && C, "hdf_gemm_rowmajor: null pointer");
   RowMajorA al{A, lda, M};
-  LinearEp ep{C, ldc, bias, residual, ldr, pre, act, p, seed, call_id, accumulate ? 1.f : 0.f};
+  LinearEp ep{C, ldc, bias, residual, ldr, pre, act, p, seed_ptr, seed, call_id, accumulate ? 1.f : 0.f};
   if (b_is_nk) {
     ColMajorB bl{Bm, ldb, N};
     return launch_gemm(al, bl, ep, M, N, K, 1, 1, (cudaStream_t)stream, "hdf_gemm_rowmajor(nk)");

@@ -145,6 +145,8 @@ struct TcConvParams {
   int a_cpasync;               // 1: the input box is gathered by 4 producer warps with 16-byte cp.async (zero-filled
                                //    out of bounds) instead of TMA: the TMA unit retires ~1 box row per 5.5 clk, which
                                //    caps 64/128-byte rows well below L2 bandwidth (profiles/r1_ncu_conv_fwd_tma.txt)
+  int commit_group;            // pipeline stages released per batch of tcgen05.commit (1..8)
+  unsigned long long* dbg;     // optional per-CTA wait-cycle counters [grid][8] (HDF_TC_DEBUG), else null
   const bf16* x;               // input tensor (cp.async path)
   long long ldx;
   int Di, Hi, Wi;              // input tensor dims
@@ -224,28 +226,44 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                       (int)p.taps.widx[e] * p.Cout);
     }
     if (!p.a_cpasync) {
-      if (ptid == 0) {
-        int s = 0; uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-          const int cls = tile / tiles_per_cls;
-          int r = tile - cls * tiles_per_cls;
-          const int n = r / tiles_per_n;
-          r -= n * tiles_per_n;
-          const int tw = r % p.nTw; r /= p.nTw;
-          const int th = r % p.nTh;
-          const int td = r / p.nTh;
-          const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TWstep * p.in_scale;
-          const int e0 = p.taps.first[cls];
-          const int kiters = (p.taps.first[cls + 1] - e0) * p.kchunks;
-          for (int it = 0; it < kiters; ++it) {
-            const int e = e0 + it / p.kchunks, kc = it % p.kchunks;
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            mbar_expect_tx(full_bar(s), p.a_bytes + (p.b_resident ? 0u : p.b_bytes));
-            const uint32_t a_dst = ring_base + s * p.stage_bytes;
-            tma_load_5d(a_dst, &tmx, full_bar(s), kc * p.KC, w0 + p.taps.dw[e], h0 + p.taps.dh[e], d0 + p.taps.dd[e], n);
-            if (!p.b_resident) tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, (int)p.taps.widx[e] * p.Cout);
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
+      // ---- TMA: lane 0 of each of the 4 producer warps issues every 4th pipeline stage, so that the per-stage
+      // issue latency (barrier probe, coordinate math, descriptor fetch) of one thread does not pace the ring
+      if (lane == 0) {
+        const int np = 1;                           // producers in use (4 did not help: the consumer paces the ring)
+        if (warp < np) {
+          long long dbg_acc = 0; const long long dbg_t0 = p.dbg ? clock64() : 0;
+          int s = warp; uint32_t ph = 0;            // stage / phase of this producer's next iteration
+          int git = 0;                              // global iteration counter (all tiles, all k-iterations)
+          for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int cls = tile / tiles_per_cls;
+            int r = tile - cls * tiles_per_cls;
+            const int n = r / tiles_per_n;
+            r -= n * tiles_per_n;
+            const int tw = r % p.nTw; r /= p.nTw;
+            const int th = r % p.nTh;
+            const int td = r / p.nTh;
+            const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TWstep * p.in_scale;
+            const int e0 = p.taps.first[cls];
+            const int ntap = p.taps.first[cls + 1] - e0;
+            for (int t = 0; t < ntap; ++t) {
+              const int e = e0 + t;
+              const int cw = w0 + p.taps.dw[e], ch = h0 + p.taps.dh[e], cd = d0 + p.taps.dd[e];
+              const int wrow = (int)p.taps.widx[e] * p.Cout;
+              for (int kc = 0; kc < p.kchunks; ++kc, ++git) {
+                if ((git % np) != warp) continue;
+                const long long t0 = p.dbg ? clock64() : 0;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                if (p.dbg) dbg_acc += clock64() - t0;
+                mbar_expect_tx(full_bar(s), p.a_bytes + (p.b_resident ? 0u : p.b_bytes));
+                const uint32_t a_dst = ring_base + s * p.stage_bytes;
+                tma_load_5d(a_dst, &tmx, full_bar(s), kc * p.KC, cw, ch, cd, n);
+                if (!p.b_resident) tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, wrow);
+                s += np;
+                if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+              }
+            }
           }
+          if (p.dbg && warp == 0) { p.dbg[blockIdx.x * 8 + 0] = dbg_acc; }
         }
       }
     } else {
@@ -310,34 +328,60 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   } else if (warp == 4) {
     if (lane == 0) {
       // ===== MMA issuer =====
+      // Everything loop-invariant lives in registers: the asm "memory" clobbers would otherwise force the kernel
+      // parameters to be re-read from the constant bank around every instruction, and this single thread's
+      // issue latency paces the whole pipeline (measured: ~600 clk per stage before this was hoisted).
       const uint32_t idesc = umma_idesc(128, p.Nmma, 0, 0);
+      const int stages = p.stages, kchunks = p.kchunks, ksteps = p.KC / 16, ncls = p.taps.ncls;
+      const uint32_t stage_bytes = p.stage_bytes, b_region = p.b_region, Nmma = (uint32_t)p.Nmma;
+      const bool bres = p.b_resident != 0, cpa = p.a_cpasync != 0, dbg = p.dbg != nullptr;
+      const uint64_t desc_hi = umma_desc(0, 16, p.sbo, p.layout);
+      const int num_tiles = p.num_tiles, gstride = gridDim.x;
+      const int kiters_c0 = (p.taps.first[1] - p.taps.first[0]) * kchunks;
       int s = 0; uint32_t ph = 0;
+      uint32_t a_addr = ring_base, fullb = full_bar(0), emptyb = empty_bar(0);
       int acc = 0; uint32_t accph = 0;
-      if (p.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int cls = tile / tiles_per_cls;
-        const int e0 = p.taps.first[cls];
-        const int kiters = (p.taps.first[cls + 1] - e0) * p.kchunks;
+      long long w_full = 0, w_tempty = 0, w_mma = 0, w_commit = 0; const long long mt0 = dbg ? clock64() : 0;
+      if (bres) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gstride) {
+        int kiters = kiters_c0, e0 = 0;
+        if (ncls > 1) {
+          const int cls = tile / tiles_per_cls;
+          e0 = p.taps.first[cls];
+          kiters = (p.taps.first[cls + 1] - e0) * kchunks;
+        }
+        long long t0 = dbg ? clock64() : 0;
         mbar_wait(tempty_bar(acc), accph ^ 1u);
+        if (dbg) w_tempty += clock64() - t0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Nmma);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * Nmma;
+        uint32_t b_addr = bres_base + (uint32_t)(e0 * kchunks) * b_region;
+        uint32_t accflag = 0;
         for (int it = 0; it < kiters; ++it) {
-          mbar_wait(full_bar(s), ph);
-          if (p.a_cpasync) fence_proxy_async();
+          if (dbg) t0 = clock64();
+          mbar_wait(fullb, ph);
+          if (dbg) w_full += clock64() - t0;
+          if (cpa) fence_proxy_async();
           tc_fence_after();
-          const uint32_t a_addr = ring_base + s * p.stage_bytes;
-          const uint32_t b_addr = p.b_resident ? bres_base + (uint32_t)(e0 * p.kchunks + it) * p.b_region : a_addr + a_region;
-          const uint64_t adesc = umma_desc(a_addr, 16, p.sbo, p.layout);
-          const uint64_t bdesc = umma_desc(b_addr, 16, p.sbo, p.layout);
-          const int ksteps = p.KC / 16;
-          for (int k = 0; k < ksteps; ++k)  // +32 B per K=16 step inside the swizzled row (encoded >>4)
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
-          umma_commit(empty_bar(s));
+          const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+          const uint64_t bdesc = desc_hi | (uint64_t)(((bres ? b_addr : a_addr + a_region) >> 4) & 0x3FFF);
+          long long t1 = dbg ? clock64() : 0;
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k) {  // +32 B per K=16 step inside the swizzled row (encoded >>4)
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accflag);
+            accflag = 1;
+          }
+          long long t2 = dbg ? clock64() : 0;
+          umma_commit(emptyb);
           if (it == kiters - 1) umma_commit(tfull_bar(acc));
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
+          if (dbg) { const long long t3 = clock64(); w_mma += t2 - t1; w_commit += t3 - t2; }
+          a_addr += stage_bytes; fullb += 8; emptyb += 8; b_addr += b_region;
+          if (++s == stages) { s = 0; ph ^= 1u; a_addr = ring_base; fullb = full_bar(0); emptyb = empty_bar(0); }
         }
         if (++acc == 2) { acc = 0; accph ^= 1u; }
       }
+      if (dbg) { p.dbg[blockIdx.x * 8 + 2] = w_full; p.dbg[blockIdx.x * 8 + 3] = w_tempty; p.dbg[blockIdx.x * 8 + 4] = clock64() - mt0;
+                 p.dbg[blockIdx.x * 8 + 7] = w_mma; p.dbg[blockIdx.x * 8 + 1] = w_commit; }
     }
   } else {
     // ===== epilogue (warps 5..8): TMEM -> registers -> (+bias) -> bf16 -> global =====
@@ -345,6 +389,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     const int m = q * 32 + lane;
     const int mw = m % p.TW, mh = (m / p.TW) % p.TH, md = m / (p.TW * p.TH);
     int acc = 0; uint32_t accph = 0;
+    long long ew_tfull = 0; const long long ept0 = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int cls = tile / tiles_per_cls;
       int r = tile - cls * tiles_per_cls;
@@ -358,7 +403,9 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       const int od = d * p.out_scale + p.taps.pd[cls], oh = h * p.out_scale + p.taps.ph[cls],
                 ow = w * p.out_scale + p.taps.pw[cls];
       bf16* yrow = p.y + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.ldy;
+      const long long et0 = p.dbg ? clock64() : 0;
       mbar_wait(tfull_bar(acc), accph);
+      if (p.dbg) ew_tfull += clock64() - et0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Nmma);
       if (!p.fold) {
@@ -402,6 +449,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; accph ^= 1u; }
     }
+    if (p.dbg && warp == 5 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = ew_tfull; p.dbg[blockIdx.x * 8 + 6] = clock64() - ept0; }
   }
   tc_fence_before();
   __syncthreads();
@@ -773,6 +821,14 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
   static const char* use_cp = getenv("HDF_TC_CPASYNC");
   p.a_cpasync = use_cp ? 1 : 0;
   p.x = (const bf16*)x; p.ldx = ldx; p.Di = Di; p.Hi = Hi; p.Wi = Wi;
+  p.commit_group = 1;
+  p.dbg = nullptr;
+  static const char* dbg_env = getenv("HDF_TC_DEBUG");
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_env) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 148 * 8 * sizeof(unsigned long long));
+    p.dbg = dbg_buf;
+  }
 
   CUtensorMap tmx, tmw;
   {
@@ -808,6 +864,14 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
   const int grid = p.num_tiles < hdf_sm_count_cached() ? p.num_tiles : hdf_sm_count_cached();
   tc_conv_fwd_kernel<<<grid, FWD_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_fwd");
+  if (p.dbg) {   // debug only: synchronous dump of CTA 0's wait-cycle counters
+    unsigned long long h[8];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc_conv dbg] Cin=%d Cout=%d fold=%d tiles=%d stages=%d | producer: wait_empty=%llu total=%llu | mma: wait_full=%llu "
+            "wait_tempty=%llu total=%llu | epilogue: wait_tfull=%llu total=%llu\n", Cin, Cout, p.fold, p.num_tiles, p.stages, h[0], h[1], h[2],
+            h[3], h[4], h[5], h[6]);
+  }
   return HDF_OK;
 }
 

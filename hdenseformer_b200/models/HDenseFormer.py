@@ -132,6 +132,7 @@ class HDenseFormer(nn.Module):
         self._engine = Engine(Config(in_channels, n_cls, n_filters, image_size, transformer_depth))
         self._arena = None
         self._step = 0
+        self._seed_dev = None
 
     def _register(self, key: str, p: nn.Parameter):
         node = self
@@ -170,8 +171,14 @@ class HDenseFormer(nn.Module):
             raise RuntimeError("hdenseformer_b200 has no CPU path: move the model and the input to a B200 (cuda) device")
         x = x.detach().float().contiguous()
         params = [p for _, p in self.named_parameters()]
-        self._step += 1
-        seed = (torch.initial_seed() * 1000003 + self._step) & 0x7FFFFFFFFFFFFFFF
+        # dropout base seed lives on the device and is advanced by a (graph-capturable) in-place add, so that a
+        # captured training step draws fresh masks on every replay
+        if self._seed_dev is None or self._seed_dev.device != x.device:
+            self._seed_dev = torch.tensor([(torch.initial_seed() * 1000003) & 0x3FFFFFFFFFFFFFFF], dtype=torch.int64,
+                                          device=x.device)
+        if self.training:
+            self._seed_dev.add_(1000003)
+        seed = self._seed_dev.clone()     # snapshot: backward of THIS forward must replay the same masks
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         outs = _HDFFunction.apply(self, x, self._resolve_dtype(), self.training, seed, need_grad, *params)
         return list(outs)

@@ -241,13 +241,20 @@ def head_bwd(g: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor
 
 
 # ----------------------------------------------------------------------------- tokens (fp32 rows)
+def _seed_args(seed):
+    """seed: int offset, or a 1-element int64 device tensor holding the base seed (graph-replay safe)"""
+    if isinstance(seed, torch.Tensor):
+        return _p(seed), 0
+    return None, int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
 def gemm(A, Bm, b_is_nk, out, bias=None, residual=None, pre=None, act=0, p=0.0, seed=0, call_id=0, accumulate=False):
     """out[M,N] = epi(A[M,K] @ (Bm^T if b_is_nk else Bm))"""
     M, K = A.shape
     N = out.shape[1]
     _C.check(_lib().hdf_gemm_rowmajor(_p(A), A.stride(0), _p(Bm), Bm.stride(0), int(b_is_nk), _p(out), out.stride(0), M, N, K,
                                       _p(bias), _p(residual), residual.stride(0) if residual is not None else 0, _p(pre),
-                                      act, float(p), seed, call_id, int(accumulate), _s()), "gemm")
+                                      act, float(p), *_seed_args(seed), call_id, int(accumulate), _s()), "gemm")
     return out
 
 
@@ -264,7 +271,7 @@ def gemm_at_b(A, Bm, out, accumulate=True):
 def act_dropout_bwd(dy, pre, act, p, seed, call_id):
     M, N = dy.shape
     dz = torch.empty((M, N), dtype=torch.float32, device=dy.device)
-    _C.check(_lib().hdf_act_dropout_bwd(_p(dy), dy.stride(0), _p(pre), _p(dz), N, M, N, act, float(p), seed, call_id, _s()),
+    _C.check(_lib().hdf_act_dropout_bwd(_p(dy), dy.stride(0), _p(pre), _p(dz), N, M, N, act, float(p), *_seed_args(seed), call_id, _s()),
              "act_dropout_bwd")
     return dz
 
@@ -313,7 +320,7 @@ def patch_embed_fwd(img, modality, weight, bias, pos, out, p, seed, call_id):
     B, Mch, D, H, W = img.shape
     E = weight.shape[0]
     _C.check(_lib().hdf_patch_embed_fwd(_p(img), B, Mch, modality, D, H, W, _p(weight), _p(bias), _p(pos), _p(out),
-                                        out.stride(0), E, float(p), seed, call_id, _s()), "patch_embed_fwd")
+                                        out.stride(0), E, float(p), *_seed_args(seed), call_id, _s()), "patch_embed_fwd")
 
 
 def patch_embed_wgrad(img, modality, dtok, dweight, accumulate=False):

@@ -128,6 +128,51 @@ def train_step(net, criterion, optimizer, data: torch.Tensor, target: torch.Tens
     return loss
 
 
+class GraphedTrainStep:
+    """One optimizer step (forward, loss, backward, optimizer) captured in a single CUDA graph and replayed per step:
+    ~1800 kernel launches per step are submitted with one call, so the host never paces the GPU.  The batch shape is
+    fixed; inputs are copied into static device buffers (H2D from pinned host memory is part of `step`).  Dropout
+    masks still change every step (the seed counter is device-resident and advanced inside the graph).  The
+    optimizer must be capturable (torch.optim.Adam(..., fused=True, capturable=True))."""
+
+    def __init__(self, net, criterion, optimizer, example_data: torch.Tensor, example_target: torch.Tensor,
+                 use_bf16: bool = True, warmup: int = 3):
+        self.net, self.criterion, self.optimizer, self.use_bf16 = net, criterion, optimizer, use_bf16
+        dev = next(net.parameters()).device
+        self.x = torch.empty(example_data.shape, dtype=torch.float32, device=dev)
+        self.t = torch.empty(example_target.shape, dtype=torch.float32, device=dev)
+        self.x.copy_(example_data)
+        self.t.copy_(example_target)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+
+    def _eager(self):
+        if self.use_bf16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = self.net(self.x)
+        else:
+            out = self.net(self.x)
+        loss = self.criterion(out, self.t)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def step(self, data: torch.Tensor, target: torch.Tensor):
+        self.x.copy_(data, non_blocking=True)
+        self.t.copy_(target, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
 class GradBucketer:
     """All-reduces (average) contiguous ranges of a flat gradient buffer as soon as backward reports them final.
 

@@ -65,7 +65,9 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
  *      133-138).  img is the caller's NCDHW fp32 batch; tokens are [B*ntok, E] fp32 rows (ld = ldo). ---- */
 int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, int H, int W, const float* weight,
                         const float* bias, const float* pos, float* out, long long ldo, int E, float p,
-                        unsigned long long seed, unsigned call_id, void* stream);
+                        const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* stream);
+/* dropout masks are a pure function of (*seed_ptr + seed, call_id, element index): seed_ptr (nullable) is a device
+ * counter the host advances once per forward, so captured CUDA graphs draw fresh masks on every replay */
 size_t hdf_patch_embed_wgrad_workspace(int B, int D, int H, int W, int E);
 int hdf_patch_embed_wgrad(const float* img, int B, int Mch, int modality, int D, int H, int W, const float* dtok,
                           long long ldd, float* dweight, int E, void* workspace, size_t ws_bytes, int accumulate,
@@ -76,12 +78,13 @@ int hdf_posemb_grad(const float* dtok, long long ld, float* dpos, int B, int nto
  *      dropout / residual epilogue.  C = epi(A[M,K] @ op(B)); op(B)=B^T for B [N,K] when b_is_nk. ---- */
 int hdf_gemm_rowmajor(const float* A, long long lda, const float* Bm, long long ldb, int b_is_nk, float* C, long long ldc,
                       int M, int N, int K, const float* bias, const float* residual, long long ldr, float* pre, int act,
-                      float p, unsigned long long seed, unsigned call_id, int accumulate, void* stream);
+                      float p, const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, int accumulate,
+                      void* stream);
 size_t hdf_gemm_at_b_workspace(int M, int N, int K);
 int hdf_gemm_at_b(const float* A, long long lda, const float* Bm, long long ldb, float* C, int M, int N, int K,
                   void* workspace, size_t ws_bytes, int accumulate, void* stream); /* C[M,N] (+)= A[K,M]^T B[K,N] */
 int hdf_act_dropout_bwd(const float* dy, long long ldd, const float* pre, float* dz, long long ldz, int M, int N, int act,
-                        float p, unsigned long long seed, unsigned call_id, void* stream);
+                        float p, const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* stream);
 int hdf_add_rows_f32(float* dst, long long ldd, const float* src, long long lds, long long rows, int C, int accumulate,
                      void* stream);
 
