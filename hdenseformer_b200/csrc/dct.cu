@@ -67,12 +67,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
+// one warp per channel, lanes stride over the per-block partials (fixed order -> deterministic)
 __global__ void ln_param_finalize_kernel(const float* __restrict__ partial, int blocks, int C, float* __restrict__ dgamma,
                                          float* __restrict__ dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (c >= C) return;
   float a = 0.f, b = 0.f;
-  for (int k = 0; k < blocks; ++k) { a += partial[(long long)k * 2 * C + c]; b += partial[(long long)k * 2 * C + C + c]; }
+  for (int k = lane; k < blocks; k += 32) { a += partial[(long long)k * 2 * C + c]; b += partial[(long long)k * 2 * C + C + c]; }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane != 0) return;
   dgamma[c] = accumulate ? dgamma[c] + a : a;
   dbeta[c] = accumulate ? dbeta[c] + b : b;
 }
@@ -290,7 +294,7 @@ int hdf_layernorm_bwd(const float* dy, long long ldd, const float* x, long long 
   layernorm_bwd_kernel<<<blocks, 256, (size_t)8 * 2 * C * sizeof(float), s>>>(dy, ldd, x, ldx, mean, rstd, gamma, dx, ldo,
                                                                               accumulate_dx, M, C, (float*)workspace);
   HDF_LAUNCH_CHECK("hdf_layernorm_bwd");
-  ln_param_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>((const float*)workspace, blocks, C, dgamma, dbeta, accumulate_params);
+  ln_param_finalize_kernel<<<cdiv((long long)C * 32, 128), 128, 0, s>>>((const float*)workspace, blocks, C, dgamma, dbeta, accumulate_params);
   HDF_LAUNCH_CHECK("hdf_layernorm_bwd/finalize");
   return HDF_OK;
 }

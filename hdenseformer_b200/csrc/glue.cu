@@ -165,9 +165,9 @@ __global__ void in_param_grads_kernel(const float* __restrict__ s1, const float*
 }
 
 int reduce_chunks(long long V, int N) {
-  // ~4 waves of CTAs, at least 1024 rows per chunk
+  // ~4 waves of CTAs, at least 128 rows per chunk (token tensors have only ~1.5 k rows)
   long long c = (4 * 148 + N - 1) / N;
-  long long mx = V / 1024 > 0 ? V / 1024 : 1;
+  long long mx = V / 128 > 0 ? V / 128 : 1;
   if (c > mx) c = mx;
   return (int)(c < 1 ? 1 : c);
 }

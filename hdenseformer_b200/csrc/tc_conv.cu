@@ -614,7 +614,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
 
 // partials [S][27][Cin][Cout] -> g[ci*sci + co*sco + tap] (+= if accumulate); fixed summation order
 __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ g, int S, int Cin, int Cout,
-                                       long long sci, long long sco, int accumulate) {
+                                       long long sci, long long sco, int accumulate, int flip) {
   const long long per = 27ll * Cin * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -622,7 +622,7 @@ __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, float* __
     const int co = i % Cout;
     const int ci = (i / Cout) % Cin;
     const int tap = i / ((long long)Cin * Cout);
-    float* q = g + ci * sci + co * sco + tap;
+    float* q = g + ci * sci + co * sco + (flip ? 26 - tap : tap);
     *q = accumulate ? (*q + s) : s;
   }
 }
@@ -933,10 +933,15 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   return passes;
 }
 
+// mode 0 with fewer output than input channels: shift dy instead of x (dW[tap] = sum_j x[j] dy[j - off(tap)]), which
+// makes the 27-times-reloaded operand the narrower one (halves L2->SMEM traffic for 64->32, 128->64, 256->128)
+static bool wgrad_swap_roles(int mode, int Cin, int Cout) { return mode == 0 && Cout < Cin && Cin <= 256; }
+
 size_t hdf_tc_wgrad_workspace(int mode, int N, int Do, int Ho, int Wo, int Cin, int Cout) {
   if (!hdf_tc_wgrad_supported(mode, Cin, Cout)) return 0;
   TcWgradParams p;
-  if (mode == 0) tc_wgrad_plan(N, Do, Ho, Wo, Cin, Cout, p);
+  if (mode == 0 && !wgrad_swap_roles(mode, Cin, Cout)) tc_wgrad_plan(N, Do, Ho, Wo, Cin, Cout, p);
+  else if (mode == 0) tc_wgrad_plan(N, Do, Ho, Wo, Cout, Cin, p);
   else tc_wgrad_plan(N, Do / 2, Ho / 2, Wo / 2, Cout, Cin, p);
   return (size_t)p.num_slabs * 27 * Cin * Cout * sizeof(float);
 }
@@ -956,12 +961,15 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
   // A side = the shifted operand whose taps are stacked along M; B side = the fixed tile (GEMM N)
   //   mode 0: A = x (shift k-1),            B = dy ; base grid = output grid
   //   mode 1: A = dy (2x res, shift 2j+k-1), B = x  ; base grid = input grid        (dW[ci][co][k] = sum_i x[i] dy[2i-1+k])
+  //   mode 0 swapped (Cout < Cin): A = dy (shift -(k-1), i.e. tap' = 26 - tap), B = x
+  const bool swap = wgrad_swap_roles(mode, Cin, Cout);
+  const bool a_is_x = (mode == 0 && !swap);
   const int D = mode == 0 ? Do : Do / 2, H = mode == 0 ? Ho : Ho / 2, W = mode == 0 ? Wo : Wo / 2;
-  const void* a_ptr = mode == 0 ? x : dy;
-  const void* b_ptr = mode == 0 ? dy : x;
-  const long long a_ld = mode == 0 ? ldx : ldy, b_ld = mode == 0 ? ldy : ldx;
-  const int Ca = mode == 0 ? Cin : Cout, Cb = mode == 0 ? Cout : Cin;
-  const long long sa = mode == 0 ? stride_ci : stride_co, sb = mode == 0 ? stride_co : stride_ci;
+  const void* a_ptr = a_is_x ? x : dy;
+  const void* b_ptr = a_is_x ? dy : x;
+  const long long a_ld = a_is_x ? ldx : ldy, b_ld = a_is_x ? ldy : ldx;
+  const int Ca = a_is_x ? Cin : Cout, Cb = a_is_x ? Cout : Cin;
+  const long long sa = a_is_x ? stride_ci : stride_co, sb = a_is_x ? stride_co : stride_ci;
   TcWgradParams p;
   const int passes = tc_wgrad_plan(N, D, H, W, Ca, Cb, p);
   p.a_scale = mode == 0 ? 1 : 2;
@@ -998,7 +1006,7 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad");
   const long long per = 27ll * Cin * Cout;
   tc_wgrad_reduce_kernel<<<min(2048, cdiv(per, 256)), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, p.num_slabs,
-                                                                                     Ca, Cb, sa, sb, accumulate);
+                                                                                     Ca, Cb, sa, sb, accumulate, swap ? 1 : 0);
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad/reduce");
   return HDF_OK;
 }

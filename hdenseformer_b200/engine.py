@@ -8,6 +8,7 @@ recomputed from a counter-based RNG instead of being stored.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional
 
 import torch
@@ -78,6 +79,17 @@ class Engine:
     def __init__(self, cfg: Config):
         self.cfg = cfg
         self.use_tc = True   # tcgen05 convolution path when available (bf16 only)
+        # The transformer branch is ~1100 tiny latency-bound launches; it runs on a second stream next to the big
+        # full-resolution convolutions (forward: encoder level 1; backward: the last two encoder blocks).
+        self.use_side_stream = True
+        self._side = {}
+        self._keep_alive = None
+
+    def _side_stream(self, dev):
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=dev)
+        return self._side[key]
 
     # ------------------------------------------------------------------ conv helpers
     def _conv_fwd(self, x, w, bias, out, mode=0):
@@ -132,7 +144,7 @@ class Engine:
             ops.conv3d_wgrad(x, dy, dw, Cout * 27, 27, 1)
 
     # ------------------------------------------------------------------ BasicConv3d / UpConv
-    def _cnr_fwd(self, c: Ctx, name, x, P, out=None, residual=None, affine=True, bias=False):
+    def _cnr_fwd(self, c: Ctx, name, x, P, out=None, residual=None, affine=True, bias=False, before_apply=None):
         """conv k3 -> InstanceNorm(+affine) -> ReLU (+ residual).  Saves raw conv output + stats."""
         wkey = f"{name}.conv.weight" if affine else f"{name}.double_conv.0.weight"
         w = P[wkey]
@@ -144,6 +156,8 @@ class Engine:
             out = torch.empty_like(y)
         g = P[f"{name}.norm.weight"] if affine else None
         b = P[f"{name}.norm.bias"] if affine else None
+        if before_apply is not None:
+            residual = before_apply()
         ops.instnorm_apply(y, mean, rstd, g, b, out, residual=residual, relu=True)
         setattr(c, name, (x, y, mean, rstd))
         return out
@@ -302,6 +316,12 @@ class Engine:
         def empty(shape, dt=dtype):
             return torch.empty(shape, dtype=dt, device=dev)
 
+        main_stream = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev) if self.use_side_stream else None
+        if side is not None:
+            side.wait_stream(main_stream)                                   # fork
+        branch_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+        branch_ctx.__enter__()
         # ---------------- transformer branches (fp32 tokens), one per modality
         d16 = cfg.tok_grid
         ntok = cfg.ntok
@@ -350,6 +370,13 @@ class Engine:
         at1 = upconv("up1", attnout)
         at2 = upconv("up2", at1)
         at3 = upconv("up3", at2)
+        branch_ctx.__exit__(None, None, None)
+        self._keep_alive = (attnall, attnout, at1, at2, at3)   # produced on the side stream, consumed on the main one
+
+        def join_at3():
+            if side is not None:
+                main_stream.wait_stream(side)                                   # join before the first consumer
+            return at3
 
         # ---------------- encoder; skip tensors are written straight into the decoder concat buffers
         pad = 16 if (self.use_tc and dtype == torch.bfloat16 and M < 16 and ops.tc_supported(0, 16, nf)) else 0
@@ -360,7 +387,7 @@ class Engine:
         cat3 = empty((B, D // 4, H // 4, W // 4, 8 * nf))
         c.cat1, c.cat2, c.cat3 = cat1, cat2, cat3
         a = self._cnr_fwd(c, "block_1_1_left", xcl, P)
-        ds0 = self._cnr_fwd(c, "block_1_2_left", a, P, out=cat1[..., nf:], residual=at3)
+        ds0 = self._cnr_fwd(c, "block_1_2_left", a, P, out=cat1[..., nf:], before_apply=join_at3)
         p1 = ops.maxpool2_fwd(ds0, empty((B, D // 2, H // 2, W // 2, nf)))
         a = self._cnr_fwd(c, "block_2_1_left", p1, P)
         ds1 = self._cnr_fwd(c, "block_2_2_left", a, P, out=cat2[..., 2 * nf:], residual=at2)
@@ -455,9 +482,16 @@ class Engine:
         dp1 = self._cnr_bwd(c, "block_2_1_left", dA, P, G)
         dds0 = dcat1[..., nf:]
         ops.maxpool2_bwd(c.cat1[..., nf:], dp1, dds0, True)
+        main_stream = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev) if self.use_side_stream else None
+        if side is not None:
+            side.wait_stream(main_stream)       # fork: the up path + transformer backward only need dds0/dds1/dds2/dx4
         dA = self._cnr_bwd(c, "block_1_2_left", dds0, P, G)
         self._cnr_bwd(c, "block_1_1_left", dA, P, G, need_dx=False)
-        notify("block_1_1_left.norm.bias")
+        if side is None:
+            notify("block_1_1_left.norm.bias")
+        branch_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+        branch_ctx.__enter__()
 
         # ---- transformer-feature up path: at3 <- up3 <- at2 <- up2 <- at1 <- up1 <- attnout <- deep_conv <- attnall
         def upconv_bwd(name, dup, extra):
@@ -474,7 +508,8 @@ class Engine:
         dat1 = upconv_bwd("up2", dat2, dds2)
         dattnout = upconv_bwd("up1", dat1, dx4)
         dattnall = upconv_bwd("deep_conv", dattnout, None)
-        notify("deep_conv.double_conv.0.bias")
+        if side is None:
+            notify("deep_conv.double_conv.0.bias")
 
         # ---- transformer branches
         R = B * cfg.ntok
@@ -498,4 +533,9 @@ class Engine:
             ops.posemb_grad(dpe, G[pre + "position_embeddings"], B, cfg.ntok, E)
             ops.colsum(dpe, G[pre + "patch_embeddings.bias"])
             ops.patch_embed_wgrad(c.x, i, dpe, G[pre + "patch_embeddings.weight"])
-            notify([k for k in G if k.startswith(pre)][-1])
+            if side is None:
+                notify([k for k in G if k.startswith(pre)][-1])
+        branch_ctx.__exit__(None, None, None)
+        if side is not None:
+            main_stream.wait_stream(side)       # join; the remaining gradient buckets are released together
+            notify([k for k in G][-1])
