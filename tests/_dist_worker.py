@@ -1,0 +1,66 @@
+"""torchrun worker for tests/test_gpu_multi.py: data-parallel gradient equality and sharded sliding window."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import hdf_oracle as O  # noqa: E402
+from hdenseformer_b200 import trainer as T  # noqa: E402
+from hdenseformer_b200.loss import CEPlusDice, DeepSuperloss  # noqa: E402
+from hdenseformer_b200.models import HDenseFormer  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    size, td, nf = (32, 32, 32), 4, 8
+    shapes = O.param_shapes(2, 2, nf, size, td)
+    sd = O.synth_state_dict(shapes, seed=7)
+    crit = DeepSuperloss(CEPlusDice(ignore_index=0))
+    x, t = O.synth_petct(world, size, seed=21), O.synth_label(world, 2, size, seed=21)
+
+    # reference: the whole batch on one GPU (what nn.DataParallel's gathered loss differentiates)
+    ref = HDenseFormer(2, 2, nf, size, td)
+    ref.load_state_dict(sd)
+    ref = ref.to(dev).eval()
+    crit(ref(x.to(dev)), t.to(dev)).backward()
+    ref_g = {k: p.grad.clone() for k, p in ref.named_parameters()}
+
+    net = HDenseFormer(2, 2, nf, size, td)
+    if rank == 0:
+        net.load_state_dict(sd)          # other ranks start from their own random init: the trainer must broadcast
+    net = net.to(dev).eval()
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)
+    dp = T.DataParallelTrainer(net, crit, opt, use_bf16=False, min_bucket_elems=1 << 12)
+    loss = dp.step(x[rank:rank + 1], t[rank:rank + 1])
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k, p in net.named_parameters():
+        den = ref_g[k].abs().max().item()
+        if den < 1e-6:
+            continue
+        worst = max(worst, (p.grad - ref_g[k]).abs().max().item() / den)
+    assert worst < 2e-4, f"rank {rank}: data-parallel gradient differs from the single-GPU batch gradient: {worst}"
+    assert len(dp._bucketer.ranges) >= 2 or dp._bucketer.prev == 0
+
+    # sharded sliding window == serial sliding window
+    vol = O.synth_petct(1, (48, 40, 32), seed=11)[0]
+    mask, prob = T.inference_slidingwindow(net, vol, 2, size, (16, 16, 16), use_bf16=False, return_prob=True)
+    dist.barrier()
+    if rank == 0:
+        ref_mask, ref_prob = O.sliding_window(lambda d: O.forward(sd, d, td)[0], vol, 2, size, (16, 16, 16))
+        err = ((prob.cpu() - ref_prob[0]).abs().max() / ref_prob.abs().max()).item()
+        assert err < 1e-4, err
+        assert O.mask_dice(mask.cpu(), ref_mask, 2) > 0.9999
+        print(f"DIST_OK world={world} grad_err={worst:.2e} sw_err={err:.2e} loss={loss.item():.5f}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
