@@ -141,6 +141,10 @@ struct TcConvParams {
   int fold;                    // 1: the three kw taps are folded into the MMA N dimension (N = 3*Cout) and
                                //    recombined across TMEM lanes (rows) in the epilogue with warp shuffles
   int Nmma;                    // MMA N = accumulator columns (Cout, or 3*Cout when folded)
+  int khfold;                  // 1 (fold mode, resident weights, TD == 1): the box carries TH+2 lines and the three kh
+                               //   taps are three MMA groups reading the same box at line-aligned row offsets, so a
+                               //   tile needs 3 pipeline stages (kd) instead of 9
+  uint32_t line_bytes;         // TW * KC * 2
   int b_resident;              // 1: all weight tiles stay resident in shared memory for the whole kernel
   int a_cpasync;               // 1: the input box is gathered by 4 producer warps with 16-byte cp.async (zero-filled
                                //    out of bounds) instead of TMA: the TMA unit retires ~1 box row per 5.5 clk, which
@@ -182,7 +186,8 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   const int ntaps_total = p.taps.first[p.taps.ncls];
   // smem: [resident weight tiles] [stage ring] [barriers]
   const uint32_t bres_base = smem_base;
-  const uint32_t ring_base = smem_base + (p.b_resident ? (uint32_t)(ntaps_total * p.kchunks) * p.b_region : 0u);
+  const uint32_t ring_base =
+      smem_base + (p.b_resident ? (uint32_t)((p.khfold ? 9 : ntaps_total) * p.kchunks) * p.b_region : 0u);
   const uint32_t bar_base = ring_base + p.stages * p.stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -219,11 +224,12 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     // ===== producers =====
     const int ptid = threadIdx.x;   // 0..127
     if (ptid == 0 && p.b_resident) {
-      mbar_expect_tx(bres_bar, (uint32_t)(ntaps_total * p.kchunks) * p.b_bytes);
-      for (int e = 0; e < ntaps_total; ++e)
+      const int nres = p.khfold ? 9 : ntaps_total;      // resident weight tiles: one per (kd,kh) in kh-fold mode
+      mbar_expect_tx(bres_bar, (uint32_t)(nres * p.kchunks) * p.b_bytes);
+      for (int e = 0; e < nres; ++e)
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_2d(bres_base + (uint32_t)(e * p.kchunks + kc) * p.b_region, &tmw, bres_bar, kc * p.KC,
-                      (int)p.taps.widx[e] * p.Cout);
+                      (p.khfold ? e * 3 : (int)p.taps.widx[e]) * p.Cout);
     }
     if (!p.a_cpasync) {
       // ---- TMA: lane 0 of each of the 4 producer warps issues every 4th pipeline stage, so that the per-stage
@@ -334,7 +340,8 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       const uint32_t idesc = umma_idesc(128, p.Nmma, 0, 0);
       const int stages = p.stages, kchunks = p.kchunks, ksteps = p.KC / 16, ncls = p.taps.ncls;
       const uint32_t stage_bytes = p.stage_bytes, b_region = p.b_region, Nmma = (uint32_t)p.Nmma;
-      const bool bres = p.b_resident != 0, cpa = p.a_cpasync != 0, dbg = p.dbg != nullptr;
+      const bool bres = p.b_resident != 0, cpa = p.a_cpasync != 0, dbg = p.dbg != nullptr, khfold = p.khfold != 0;
+      const uint32_t line_bytes = p.line_bytes;
       const uint64_t desc_hi = umma_desc(0, 16, p.sbo, p.layout);
       const int num_tiles = p.num_tiles, gstride = gridDim.x;
       const int kiters_c0 = (p.taps.first[1] - p.taps.first[0]) * kchunks;
@@ -363,13 +370,30 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
           if (dbg) w_full += clock64() - t0;
           if (cpa) fence_proxy_async();
           tc_fence_after();
-          const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
-          const uint64_t bdesc = desc_hi | (uint64_t)(((bres ? b_addr : a_addr + a_region) >> 4) & 0x3FFF);
           long long t1 = dbg ? clock64() : 0;
+          if (!khfold) {
+            const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+            const uint64_t bdesc = desc_hi | (uint64_t)(((bres ? b_addr : a_addr + a_region) >> 4) & 0x3FFF);
 #pragma unroll 4
-          for (int k = 0; k < ksteps; ++k) {  // +32 B per K=16 step inside the swizzled row (encoded >>4)
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accflag);
-            accflag = 1;
+            for (int k = 0; k < ksteps; ++k) {  // +32 B per K=16 step inside the swizzled row (encoded >>4)
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accflag);
+              accflag = 1;
+            }
+          } else {
+            // it = kd * kchunks + kc ; kh = 0,1,2 reads box lines kh .. kh+TH-1 (row offset kh * TW rows, a multiple
+            // of the 8-row swizzle atom) against the resident weight tile (kd, kh, kc)
+            const int kd = it / kchunks, kc = it - kd * kchunks;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + (uint32_t)kh * line_bytes) >> 4) & 0x3FFF);
+              const uint32_t bt = bres_base + (uint32_t)(((kd * 3 + kh) * kchunks + kc)) * b_region;
+              const uint64_t bdesc = desc_hi | (uint64_t)((bt >> 4) & 0x3FFF);
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) {
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accflag);
+                accflag = 1;
+              }
+            }
           }
           long long t2 = dbg ? clock64() : 0;
           umma_commit(emptyb);
@@ -806,6 +830,21 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
   const size_t bres_bytes = (size_t)ntaps_total * p.kchunks * p.b_region;
   static const char* no_res = getenv("HDF_TC_NO_RESIDENT");
   p.b_resident = (bres_bytes <= 114 * 1024 && !no_res) ? 1 : 0;
+  p.khfold = 0;
+  p.line_bytes = (uint32_t)p.TW * p.KC * 2u;
+  static const char* no_kh = getenv("HDF_TC_NO_KHFOLD");
+  if (p.fold && p.b_resident && !no_kh) {
+    // kh-fold: one box of TH+2 lines per kd; needs all lines of the tile in one d-plane
+    const int lines = 128 / p.TW;
+    p.khfold = 1;
+    p.TH = lines; p.TD = 1;
+    p.nTd = D; p.nTh = cdiv(H, lines);
+    p.num_tiles = N * p.nTd * p.nTh * p.nTw;
+    memset(&p.taps, 0, sizeof(p.taps));
+    p.taps.ncls = 1; p.taps.first[0] = 0; p.taps.first[1] = 3;
+    for (int e = 0; e < 3; ++e) { p.taps.dd[e] = (signed char)(e - 1); p.taps.dh[e] = -1; p.taps.dw[e] = -1; p.taps.widx[e] = (signed char)(e * 9); }
+    p.a_bytes = (uint32_t)p.TW * (lines + 2) * p.KC * 2u;
+  }
   const uint32_t a_region_h = (p.a_bytes + 1023u) & ~1023u;
   p.stage_bytes = a_region_h + (p.b_resident ? 0u : p.b_region);
   const size_t ring_budget = 200 * 1024 - (p.b_resident ? bres_bytes : 0);
@@ -836,7 +875,8 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
     cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)N};
     cuuint64_t gstr[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)Wi * ldx * 2, (cuuint64_t)Hi * Wi * ldx * 2,
                           (cuuint64_t)Di * Hi * Wi * ldx * 2};
-    cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)p.TW * es, (cuuint32_t)p.TH * es, (cuuint32_t)p.TD * es, 1};
+    cuuint32_t box[5] = {(cuuint32_t)p.KC, (cuuint32_t)p.TW * es, (cuuint32_t)(p.TH + (p.khfold ? 2 : 0)) * es,
+                         (cuuint32_t)p.TD * es, 1};
     cuuint32_t estr[5] = {1, es, es, es, 1};
     CUresult r = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(inner), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -853,6 +893,7 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { hdf_set_error("hdf_tc_conv3d_fwd: encode(w) failed: %d", (int)r); return HDF_ERR_CUDA; }
   }
+  // (kh-fold reads up to 2 lines past the 128 rows of the last MMA window: they are inside the stage's box)
   const size_t smem = (p.b_resident ? bres_bytes : 0) + (size_t)p.stages * p.stage_bytes + 1024 /*align slack*/ +
                       8 * (2 * p.stages + 6) + 64;
   static size_t configured = 0;
