@@ -171,7 +171,7 @@ def main():
     crit = DeepSuperloss(CEPlusDice(weight=None, ignore_index=0))
     decay = [p for n_, p in net.named_parameters() if p.dim() > 1 and not n_.endswith(".bias")]
     no_decay = [p for n_, p in net.named_parameters() if not (p.dim() > 1 and not n_.endswith(".bias"))]
-    use_graph = (world == 1) and not a.no_graph
+    use_graph = not a.no_graph and (world == 1 or os.environ.get("HDF_BENCH_GRAPH_MULTI", "1") == "1")
     opt = torch.optim.Adam([{"params": decay, "weight_decay": 1e-4}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-3,
                            fused=True, capturable=use_graph)   # grouping of trainer.py:812-819
     dp = T.DataParallelTrainer(net, crit, opt, use_bf16=not a.fp32)
@@ -203,9 +203,15 @@ def main():
     if use_graph:
         try:
             graphed = T.GraphedTrainStep(net, crit, opt, devb[0][0], devb[0][1], use_bf16=not a.fp32)
+            ok = torch.tensor([1], device=dev)
         except Exception as e:   # keep the benchmark alive; the mode actually used is reported in config.launch
-            print(f"[bench] CUDA-graph capture failed, falling back to eager launches: {e!r}", file=sys.stderr)
+            print(f"[bench] rank {rank}: CUDA-graph capture failed, falling back to eager launches: {e!r}", file=sys.stderr)
             graphed = None
+            ok = torch.tensor([0], device=dev)
+        if world > 1:            # all ranks must agree on the launch mode (collectives inside / outside the graph)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                graphed = None
     stepper = graphed.step if graphed is not None else dp.step
     step_dev = lambda i: stepper(*devb[i % nb])
 

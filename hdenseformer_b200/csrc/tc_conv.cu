@@ -909,9 +909,9 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
     unsigned long long h[8];
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[tc_conv dbg] Cin=%d Cout=%d fold=%d tiles=%d stages=%d | producer: wait_empty=%llu total=%llu | mma: wait_full=%llu "
-            "wait_tempty=%llu total=%llu | epilogue: wait_tfull=%llu total=%llu\n", Cin, Cout, p.fold, p.num_tiles, p.stages, h[0], h[1], h[2],
-            h[3], h[4], h[5], h[6]);
+    fprintf(stderr, "[tc_conv dbg] Cin=%d Cout=%d fold=%d khfold=%d tiles=%d stages=%d | producer: wait_empty=%llu | mma: wait_full=%llu "
+            "wait_tempty=%llu mma_issue=%llu commit=%llu total=%llu | epilogue: wait_tfull=%llu total=%llu\n", Cin, Cout, p.fold, p.khfold,
+            p.num_tiles, p.stages, h[0], h[2], h[3], h[7], h[1], h[4], h[5], h[6]);
   }
   return HDF_OK;
 }
