@@ -280,9 +280,15 @@ def main():
             out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "volumes/s", "cores": threads, "kind": "port",
                                    "sample": f"{n} step(s) of BASELINE config[0] (1x2x96^3 fwd+loss+bwd, fp32, train mode) on "
                                              f"{threads} host threads; oracle/hdf_oracle.py"}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph holds NCCL kernels; tearing the communicator down underneath it can hang, so leave
+        # together and skip interpreter teardown
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
