@@ -47,6 +47,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (it > (1u << 26)) __trap();
   }
 }
+// one lane of a converged warp; the compiler keeps the guarded block on the uniform datapath (no per-lane loop
+// around instructions that take uniform-register operands such as tcgen05.mma / TMA)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -332,8 +339,8 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       cp_async_wait<0>();
     }
   } else if (warp == 4) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer (whole warp waits on the barriers, one elected lane issues) =====
       // Everything loop-invariant lives in registers: the asm "memory" clobbers would otherwise force the kernel
       // parameters to be re-read from the constant bank around every instruction, and this single thread's
       // issue latency paces the whole pipeline (measured: ~600 clk per stage before this was hoisted).
@@ -371,6 +378,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
           if (cpa) fence_proxy_async();
           tc_fence_after();
           long long t1 = dbg ? clock64() : 0;
+          if (elect_one_sync()) {
           if (!khfold) {
             const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
             const uint64_t bdesc = desc_hi | (uint64_t)(((bres ? b_addr : a_addr + a_region) >> 4) & 0x3FFF);
@@ -395,16 +403,19 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
               }
             }
           }
-          long long t2 = dbg ? clock64() : 0;
           umma_commit(emptyb);
           if (it == kiters - 1) umma_commit(tfull_bar(acc));
-          if (dbg) { const long long t3 = clock64(); w_mma += t2 - t1; w_commit += t3 - t2; }
+          }
+          __syncwarp();
+          accflag = 1;
+          long long t2 = dbg ? clock64() : 0;
+          if (dbg) { w_mma += t2 - t1; }
           a_addr += stage_bytes; fullb += 8; emptyb += 8; b_addr += b_region;
           if (++s == stages) { s = 0; ph ^= 1u; a_addr = ring_base; fullb = full_bar(0); emptyb = empty_bar(0); }
         }
         if (++acc == 2) { acc = 0; accph ^= 1u; }
       }
-      if (dbg) { p.dbg[blockIdx.x * 8 + 2] = w_full; p.dbg[blockIdx.x * 8 + 3] = w_tempty; p.dbg[blockIdx.x * 8 + 4] = clock64() - mt0;
+      if (dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = w_full; p.dbg[blockIdx.x * 8 + 3] = w_tempty; p.dbg[blockIdx.x * 8 + 4] = clock64() - mt0;
                  p.dbg[blockIdx.x * 8 + 7] = w_mma; p.dbg[blockIdx.x * 8 + 1] = w_commit; }
     }
   } else {
@@ -635,6 +646,192 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
+
+// ----------------------------------------------------------------------------- weight-gradient kernel, v2
+// Measured on B200 (profiles/r1_umma_probe.txt): an SS-mode tcgen05.mma with M=128 costs >= ~86-130 clk whatever N is
+// (the 128-row A operand read from shared memory), and N/2 clk of math: small N wastes the tensor core.  v2 therefore
+// puts the *shifted* operand S (27 taps x Cs channels) on the N side, up to 256 (tap, channel) columns per MMA, stacked
+// from consecutive [KV x CWs] TMA sub-tiles through the B descriptor's leading-byte-offset; the fixed operand F
+// (Cf channels, one tile per voxel chunk) is the 128-row M side (replicated sub-tiles when Cf < 128).
+//   D[f, (tap, s)] = sum_v F[v][f] * S[v + off(tap)][s]        both operands MN-major, K = voxels
+// A CTA owns one slab of voxel chunks (split-K) and one pass = the accumulators that fit 512 TMEM columns.
+struct TcWgrad2Params {
+  int N, D, H, W;
+  int Cs, Cf;
+  int TD, TH, TW, nTd, nTh, nTw;
+  int num_chunks, chunks_per_slab, num_slabs;
+  int KV;
+  int CWs, spt, total_sub, SPGn, G;      // S sub-tile width, sub-tiles per tap, total sub-tiles, sub-tiles per group, groups
+  int CWf, nsub_f, nrep_f, nMh;          // F sub-tile width, distinct sub-tiles, TMA replicas (Cf < 128), M halves
+  int groups_per_pass, mh_per_pass, passes_g, passes_m;
+  int s_stages;
+  int s_scale;                           // 1, or 2 when S is the 2x-resolution tensor (transposed conv)
+  uint32_t s_sub_bytes, s_stage_bytes, f_sub_bytes, f_stage_bytes;
+  uint32_t s_layout, s_sbo, f_layout, f_sbo;
+  uint32_t tmem_cols;
+  float* partial;                        // [num_slabs][27][Cs][Cf]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tms, const __grid_constant__ CUtensorMap tmf, const TcWgrad2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t f_base = smem_base + p.s_stages * p.s_stage_bytes;
+  const uint32_t bar_base = f_base + 2 * p.f_stage_bytes;
+  auto sfull = [&](int s) { return bar_base + 8u * s; };
+  auto sempty = [&](int s) { return bar_base + 8u * (p.s_stages + s); };
+  auto ffull = [&](int s) { return bar_base + 8u * (2 * p.s_stages + s); };
+  auto fempty = [&](int s) { return bar_base + 8u * (2 * p.s_stages + 2 + s); };
+  const uint32_t accfull = bar_base + 8u * (2 * p.s_stages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.s_stages + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int slab = blockIdx.x;
+  const int pass_g = blockIdx.y / p.passes_m, pass_m = blockIdx.y % p.passes_m;
+  const int g_begin = pass_g * p.groups_per_pass, g_end = min(p.G, g_begin + p.groups_per_pass);
+  const int h_begin = pass_m * p.mh_per_pass, h_end = min(p.nMh, h_begin + p.mh_per_pass);
+  const int c_begin = slab * p.chunks_per_slab, c_end = min(p.num_chunks, c_begin + p.chunks_per_slab);
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tms); tma_prefetch_desc(&tmf); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.s_stages; ++s) { mbar_init(sfull(s), 1); mbar_init(sempty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(ffull(s), 1); mbar_init(fempty(s), 1); }
+    mbar_init(accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int tiles_per_n = p.nTd * p.nTh * p.nTw;
+
+  if (warp == 0) {
+    // ===== TMA producer (one elected lane) =====
+    int s = 0; uint32_t ph = 0;
+    int fs = 0; uint32_t fph = 0;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int n = c / tiles_per_n;
+      int r = c - n * tiles_per_n;
+      const int tw = r % p.nTw; r /= p.nTw;
+      const int th = r % p.nTh;
+      const int td = r / p.nTh;
+      const int d0 = td * p.TD, h0 = th * p.TH, w0 = tw * p.TW;
+      const int sd0 = d0 * p.s_scale - 1, sh0 = h0 * p.s_scale - 1, sw0 = w0 * p.s_scale - 1;
+      mbar_wait(fempty(fs), fph ^ 1u);
+      if (elect_one_sync()) {
+        // the M side always spans 128 channels: [h_begin, h_end) halves of Cf, or nrep_f replicas when Cf < 128
+        const int nld = (p.Cf < 128) ? p.nrep_f * p.nsub_f : (h_end - h_begin) * (128 / p.CWf);
+        mbar_expect_tx(ffull(fs), p.f_sub_bytes * nld);
+        for (int j = 0; j < nld; ++j) {
+          const int sub = (p.Cf < 128) ? (j % p.nsub_f) : (h_begin * (128 / p.CWf) + j);
+          tma_load_5d(f_base + fs * p.f_stage_bytes + j * p.f_sub_bytes, &tmf, ffull(fs), sub * p.CWf, w0, h0, d0, n);
+        }
+      }
+      __syncwarp();
+      if (++fs == 2) { fs = 0; fph ^= 1u; }
+      for (int g = g_begin; g < g_end; ++g) {
+        const int u0 = g * p.SPGn;
+        const int nsub = min(p.SPGn, p.total_sub - u0);
+        mbar_wait(sempty(s), ph ^ 1u);
+        if (elect_one_sync()) {
+          mbar_expect_tx(sfull(s), p.s_sub_bytes * nsub);
+          for (int j = 0; j < nsub; ++j) {
+            const int u = u0 + j;
+            const int tap = u / p.spt, ch0 = (u - tap * p.spt) * p.CWs;
+            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+            tma_load_5d(smem_base + s * p.s_stage_bytes + j * p.s_sub_bytes, &tms, sfull(s), ch0, sw0 + kw, sh0 + kh, sd0 + kd, n);
+          }
+        }
+        __syncwarp();
+        if (++s == p.s_stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const int ksteps = p.KV / 16, SPGn = p.SPGn, CWs = p.CWs, total_sub = p.total_sub, s_stages = p.s_stages;
+    const uint32_t s_stage_bytes = p.s_stage_bytes, f_stage_bytes = p.f_stage_bytes;
+    const uint64_t sdesc_hi = umma_desc(0, p.s_sub_bytes, p.s_sbo, p.s_layout);
+    const uint64_t fdesc_hi = umma_desc(0, p.f_sub_bytes, p.f_sbo, p.f_layout);
+    const uint64_t s_adv = (uint64_t)((2u * p.s_sbo) >> 4), f_adv = (uint64_t)((2u * p.f_sbo) >> 4);
+    const uint32_t f_half_bytes = (p.Cf < 128) ? 0u : p.f_sub_bytes * (uint32_t)(128 / p.CWf);
+    const int nh = h_end - h_begin;
+    int s = 0; uint32_t ph = 0;
+    int fs = 0; uint32_t fph = 0;
+    for (int c = c_begin; c < c_end; ++c) {
+      mbar_wait(ffull(fs), fph);
+      tc_fence_after();
+      const uint32_t f_addr = f_base + fs * f_stage_bytes;
+      uint32_t col = 0;
+      for (int g = g_begin; g < g_end; ++g) {
+        const int nsub = min(SPGn, total_sub - g * SPGn);
+        const int Ng = nsub * CWs;
+        mbar_wait(sfull(s), ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t idesc = umma_idesc(128, Ng, 1, 1);
+          const uint64_t bdesc = sdesc_hi | (uint64_t)(((smem_base + s * s_stage_bytes) >> 4) & 0x3FFF);
+          for (int h = 0; h < nh; ++h) {
+            const uint64_t adesc = fdesc_hi | (uint64_t)(((f_addr + (uint32_t)h * f_half_bytes) >> 4) & 0x3FFF);
+            const uint32_t d_tmem = tmem_base + col + (uint32_t)(h * Ng);
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(d_tmem, adesc + f_adv * k, bdesc + s_adv * k, idesc, (c != c_begin) || (k != 0));
+          }
+          umma_commit(sempty(s));
+        }
+        __syncwarp();
+        col += (uint32_t)(nh * Ng);
+        if (++s == s_stages) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one_sync()) umma_commit(fempty(fs));
+      __syncwarp();
+      if (++fs == 2) { fs = 0; fph ^= 1u; }
+    }
+    if (elect_one_sync()) umma_commit(accfull);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===== epilogue: accumulators -> fp32 partials [tap][s][f] (lane = f: warp-coalesced stores) =====
+    const int q = warp - 4;
+    const int m = q * 32 + lane;
+    mbar_wait(accfull, 0);
+    tc_fence_after();
+    uint32_t col = 0;
+    for (int g = g_begin; g < g_end; ++g) {
+      const int nsub = min(p.SPGn, p.total_sub - g * p.SPGn);
+      const int Ng = nsub * p.CWs;
+      for (int h = h_begin; h < h_end; ++h) {
+        const int f = (p.Cf < 128) ? m : h * 128 + m;
+        const bool fvalid = (p.Cf < 128) ? (m < p.Cf) : true;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col + (uint32_t)((h - h_begin) * Ng);
+        for (int c0 = 0; c0 < Ng; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (fvalid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int cc = c0 + j;
+              const int u = g * p.SPGn + cc / p.CWs;
+              const int tap = u / p.spt;
+              const int sch = (u - tap * p.spt) * p.CWs + cc % p.CWs;
+              p.partial[(((long long)slab * 27 + tap) * p.Cs + sch) * p.Cf + f] = __uint_as_float(v[j]);
+            }
+          }
+        }
+      }
+      col += (uint32_t)((h_end - h_begin) * Ng);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 
 // partials [S][27][Cin][Cout] -> g[ci*sci + co*sco + tap] (+= if accumulate); fixed summation order
 __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ g, int S, int Cin, int Cout,
@@ -919,8 +1116,10 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
 static int wgrad_ok(int c) { return c == 16 || c == 32 || (c % 64 == 0 && c >= 64); }
 
 // the N side of the GEMM (dy channels for mode 0, x channels for the transposed conv) must fit one MMA (<= 256)
+static bool wgrad_use_v1() { static const char* e = getenv("HDF_TC_WGRAD_V1"); return e != nullptr; }
 int hdf_tc_wgrad_supported(int mode, int Cin, int Cout) {
   if (mode != 0 && mode != 1) return 0;
+  if (!wgrad_use_v1()) return wgrad_ok(Cin) && wgrad_ok(Cout);
   return wgrad_ok(Cin) && wgrad_ok(Cout) && (mode == 0 ? Cout : Cin) <= 256;
 }
 
@@ -974,12 +1173,137 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   return passes;
 }
 
+// ---- v2 planning: which operand is shifted (S, N side) and which is fixed (F, M side)
+struct Wg2Roles { bool s_is_x; int Cs, Cf, s_scale, flip; };
+static Wg2Roles wg2_roles(int mode, int Cin, int Cout) {
+  Wg2Roles r;
+  if (mode == 1) { r.s_is_x = false; r.Cs = Cout; r.Cf = Cin; r.s_scale = 2; r.flip = 0; }      // dW = sum_i x[i] dy[2i-1+k]
+  else if (Cout < Cin) { r.s_is_x = false; r.Cs = Cout; r.Cf = Cin; r.s_scale = 1; r.flip = 1; } // shift dy (tap' = 26-tap)
+  else { r.s_is_x = true; r.Cs = Cin; r.Cf = Cout; r.s_scale = 1; r.flip = 0; }
+  return r;
+}
+static int wg2_supported(int mode, int Cin, int Cout) {
+  if (mode != 0 && mode != 1) return 0;
+  return wgrad_ok(Cin) && wgrad_ok(Cout);
+}
+static int tc_wgrad2_plan(int N, int D, int H, int W, int Cs, int Cf, TcWgrad2Params& p) {
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cs = Cs; p.Cf = Cf;
+  p.KV = 64;
+  {
+    long long best = -1; p.TD = p.TH = p.TW = 1;
+    for (int tw = 1; tw <= p.KV; tw *= 2)
+      for (int th = 1; th * tw <= p.KV; th *= 2) {
+        const int td = p.KV / (tw * th);
+        const long long tiles = (long long)cdiv(D, td) * cdiv(H, th) * cdiv(W, tw);
+        if (best < 0 || tiles < best || (tiles == best && tw > p.TW)) { best = tiles; p.TD = td; p.TH = th; p.TW = tw; }
+      }
+  }
+  p.nTd = cdiv(D, p.TD); p.nTh = cdiv(H, p.TH); p.nTw = cdiv(W, p.TW);
+  p.num_chunks = N * p.nTd * p.nTh * p.nTw;
+  p.CWs = Cs < 64 ? Cs : 64;
+  p.spt = Cs / p.CWs;
+  p.total_sub = 27 * p.spt;
+  p.SPGn = 256 / p.CWs;
+  p.G = cdiv(p.total_sub, p.SPGn);
+  p.CWf = Cf < 64 ? Cf : 64;
+  p.nsub_f = Cf / p.CWf;
+  p.nrep_f = Cf < 128 ? 128 / Cf : 1;
+  p.nMh = Cf < 128 ? 1 : Cf / 128;
+  p.mh_per_pass = p.nMh < 2 ? p.nMh : 2;
+  p.groups_per_pass = p.mh_per_pass == 1 ? 2 : 1;
+  if (p.groups_per_pass > p.G) p.groups_per_pass = p.G;
+  p.passes_g = cdiv(p.G, p.groups_per_pass);
+  p.passes_m = cdiv(p.nMh, p.mh_per_pass);
+  p.s_sub_bytes = (uint32_t)p.KV * p.CWs * 2;
+  p.s_stage_bytes = p.s_sub_bytes * p.SPGn;            // KV * 512 bytes = 32 KB
+  p.f_sub_bytes = (uint32_t)p.KV * p.CWf * 2;
+  p.f_stage_bytes = p.f_sub_bytes * (128 / p.CWf) * p.mh_per_pass;
+  p.s_stages = (int)((200u * 1024u - 2u * p.f_stage_bytes) / p.s_stage_bytes);
+  if (p.s_stages > 5) p.s_stages = 5;
+  const int is = p.CWs * 2, jf = p.CWf * 2;
+  p.s_layout = is == 128 ? 2u : is == 64 ? 4u : 6u;
+  p.f_layout = jf == 128 ? 2u : jf == 64 ? 4u : 6u;
+  p.s_sbo = 8u * is;
+  p.f_sbo = 8u * jf;
+  uint32_t need = (uint32_t)(p.groups_per_pass * p.mh_per_pass * 256), cols = 32;
+  while (cols < need) cols *= 2;
+  p.tmem_cols = cols;
+  const int passes = p.passes_g * p.passes_m;
+  int slabs = cdiv(2 * hdf_sm_count_cached(), passes);
+  const int max_slabs = p.num_chunks / 16 > 0 ? p.num_chunks / 16 : 1;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  p.chunks_per_slab = cdiv(p.num_chunks, slabs);
+  p.num_slabs = cdiv(p.num_chunks, p.chunks_per_slab);
+  return passes;
+}
+
+static int tc_wgrad2_launch(int mode, const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
+                            long long stride_co, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* workspace,
+                            size_t ws_bytes, int accumulate, cudaStream_t stream) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { hdf_set_error("hdf_tc_conv3d_wgrad: cuTensorMapEncodeTiled unavailable"); return HDF_ERR_CUDA; }
+  const Wg2Roles r = wg2_roles(mode, Cin, Cout);
+  const int D = mode == 0 ? Do : Do / 2, H = mode == 0 ? Ho : Ho / 2, W = mode == 0 ? Wo : Wo / 2;   // base grid
+  TcWgrad2Params p;
+  const int passes = tc_wgrad2_plan(N, D, H, W, r.Cs, r.Cf, p);
+  p.s_scale = r.s_scale;
+  HDF_REQUIRE(ws_bytes >= (size_t)p.num_slabs * 27 * Cin * Cout * sizeof(float), "hdf_tc_conv3d_wgrad: workspace too small");
+  p.partial = (float*)workspace;
+  const void* s_ptr = r.s_is_x ? x : dy;
+  const void* f_ptr = r.s_is_x ? dy : x;
+  const long long s_ld = r.s_is_x ? ldx : ldy, f_ld = r.s_is_x ? ldy : ldx;
+  CUtensorMap tms, tmf;
+  for (int which = 0; which < 2; ++which) {
+    const void* base = which == 0 ? s_ptr : f_ptr;
+    const long long ld = which == 0 ? s_ld : f_ld;
+    const int C = which == 0 ? r.Cs : r.Cf;
+    const int cw = which == 0 ? p.CWs : p.CWf;
+    const cuuint32_t es = which == 0 ? (cuuint32_t)p.s_scale : 1u;
+    const int Dt = D * (int)es, Ht = H * (int)es, Wt = W * (int)es;
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)Dt, (cuuint64_t)N};
+    cuuint64_t gstr[4] = {(cuuint64_t)ld * 2, (cuuint64_t)Wt * ld * 2, (cuuint64_t)Ht * Wt * ld * 2,
+                          (cuuint64_t)Dt * Ht * Wt * ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)cw, (cuuint32_t)p.TW * es, (cuuint32_t)p.TH * es, (cuuint32_t)p.TD * es, 1};
+    cuuint32_t estr[5] = {1, es, es, es, 1};
+    CUresult rr = enc(which == 0 ? &tms : &tmf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rr != CUDA_SUCCESS) { hdf_set_error("hdf_tc_conv3d_wgrad: encode failed: %d", (int)rr); return HDF_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.s_stages * p.s_stage_bytes + 2 * (size_t)p.f_stage_bytes + 1024 + 8 * (2 * p.s_stages + 6) + 64;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) { hdf_set_error("hdf_tc_conv3d_wgrad: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
+    configured = true;
+  }
+  HDF_REQUIRE(smem <= 227 * 1024 && p.s_stages >= 2, "hdf_tc_conv3d_wgrad: smem plan does not fit (%zu bytes, %d stages)", smem, p.s_stages);
+  dim3 grid(p.num_slabs, passes);
+  tc_conv_wgrad2_kernel<<<grid, TC_THREADS, smem, stream>>>(tms, tmf, p);
+  HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad(v2)");
+  // partial[slab][tap][s][f] -> dw: (s,f) = (ci,co) when S is x, (co,ci) otherwise
+  const long long ss = r.s_is_x ? stride_ci : stride_co, sf = r.s_is_x ? stride_co : stride_ci;
+  const long long per = 27ll * Cin * Cout;
+  tc_wgrad_reduce_kernel<<<min(2048, cdiv(per, 256)), 256, 0, stream>>>((const float*)workspace, dw, p.num_slabs, r.Cs, r.Cf, ss,
+                                                                      sf, accumulate, r.flip);
+  HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad(v2)/reduce");
+  return HDF_OK;
+}
+
 // mode 0 with fewer output than input channels: shift dy instead of x (dW[tap] = sum_j x[j] dy[j - off(tap)]), which
 // makes the 27-times-reloaded operand the narrower one (halves L2->SMEM traffic for 64->32, 128->64, 256->128)
 static bool wgrad_swap_roles(int mode, int Cin, int Cout) { return mode == 0 && Cout < Cin && Cin <= 256; }
 
 size_t hdf_tc_wgrad_workspace(int mode, int N, int Do, int Ho, int Wo, int Cin, int Cout) {
   if (!hdf_tc_wgrad_supported(mode, Cin, Cout)) return 0;
+  if (!wgrad_use_v1()) {
+    const Wg2Roles r = wg2_roles(mode, Cin, Cout);
+    TcWgrad2Params q;
+    if (mode == 0) tc_wgrad2_plan(N, Do, Ho, Wo, r.Cs, r.Cf, q);
+    else tc_wgrad2_plan(N, Do / 2, Ho / 2, Wo / 2, r.Cs, r.Cf, q);
+    return (size_t)q.num_slabs * 27 * Cin * Cout * sizeof(float);
+  }
   TcWgradParams p;
   if (mode == 0 && !wgrad_swap_roles(mode, Cin, Cout)) tc_wgrad_plan(N, Do, Ho, Wo, Cin, Cout, p);
   else if (mode == 0) tc_wgrad_plan(N, Do, Ho, Wo, Cout, Cin, p);
@@ -997,6 +1321,9 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
   HDF_REQUIRE(x && dy && dw && workspace, "hdf_tc_conv3d_wgrad: null pointer");
   HDF_REQUIRE((ldx % 8 == 0) && (ldy % 8 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0),
               "hdf_tc_conv3d_wgrad: operands must be 16-byte aligned with channel strides multiple of 8");
+  if (!wgrad_use_v1())
+    return tc_wgrad2_launch(mode, x, ldx, dy, ldy, dw, stride_ci, stride_co, N, Do, Ho, Wo, Cin, Cout, workspace, ws_bytes,
+                            accumulate, (cudaStream_t)stream);
   EncodeTiledFn enc = get_encode();
   if (!enc) { hdf_set_error("hdf_tc_conv3d_wgrad: cuTensorMapEncodeTiled unavailable"); return HDF_ERR_CUDA; }
   // A side = the shifted operand whose taps are stacked along M; B side = the fixed tile (GEMM N)

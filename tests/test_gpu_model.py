@@ -167,3 +167,34 @@ def test_sliding_window_matches_oracle():
     assert rel(prob, ref_prob[0]) < 1e-4
     assert (mask.cpu() != ref_mask).sum().item() == 0
     assert O.mask_dice(mask.cpu(), ref_mask, 2) == 1.0
+
+
+@pytest.mark.parametrize("in_ch,n_cls,size,batch", [(3, 2, (16, 48, 96), 1), (4, 4, (32, 32, 48), 2)])
+def test_bf16_tensor_core_path_other_configs(in_ch, n_cls, size, batch):
+    """BASELINE configs 3/4 in miniature (anisotropic 3-modality MR; 4-modality, 4-class, batch 2, deep supervision)
+    with nf=16 so every conv takes the tcgen05 path.  These miniature volumes have only 18-24 tokens, so the deep
+    InstanceNorms normalise over a handful of voxels and bf16 rounding is amplified (SURVEY 8c pitfall 2: the
+    reference's own bf16 autocast is at 1.4e-2 on such sizes); the 2e-2 north-star gate is asserted at 64^3 in
+    test_fp32_and_bf16_vs_oracle_64cube, here the bound is 3e-2 plus gradient alignment with the exact fp32 path."""
+    td, nf = 4, 16
+    m, sd = build(in_ch, n_cls, nf, size, td)
+    m.eval()
+    x = O.synth_mr(batch, in_ch, size, seed=4)
+    tgt = O.synth_label(batch, n_cls, size, seed=4)
+    ref = O.forward(sd, x, td)
+    crit = DeepSuperloss(CEPlusDice(ignore_index=0))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        outs = m(x.to(DEV))
+    assert outs[0].dtype == torch.bfloat16 and tuple(outs[3].shape) == (batch, n_cls, *(s // 8 for s in size))
+    for o, r in zip(outs, ref):
+        assert rel(o, r) < 3e-2, rel(o, r)
+    crit(outs, tgt.to(DEV)).backward()
+    g16 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    crit(m(x.to(DEV)), tgt.to(DEV)).backward()
+    big = [k for k, p in m.named_parameters() if p.numel() >= 4096 and k not in ZERO_GRAD_KEYS]
+    cos = []
+    for k in big:
+        a, b = g16[k].double().flatten(), dict(m.named_parameters())[k].grad.double().flatten()
+        cos.append((a @ b).item() / max(a.norm().item() * b.norm().item(), 1e-30))
+    assert min(cos) > 0.95 and sum(cos) / len(cos) > 0.99, (min(cos), sum(cos) / len(cos))
