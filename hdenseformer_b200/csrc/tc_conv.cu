@@ -587,31 +587,40 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer (whole warp waits, one elected lane issues) =====
       const uint32_t idesc = umma_idesc(128, p.Cout, 1, 1);   // both operands MN-major (K = voxel rows)
       int s = 0; uint32_t ph = 0;
       int bs = 0; uint32_t bph = 0;
-      const int ksteps = p.KV / 16;
+      const int ksteps = p.KV / 16, a_stages = p.a_stages, Cout = p.Cout;
+      const uint32_t a_stage_bytes = p.a_stage_bytes, b_stage_bytes = p.b_stage_bytes;
+      const uint64_t adesc_hi = umma_desc(0, p.a_sub_bytes, p.a_sbo, p.a_layout);
+      const uint64_t bdesc_hi = umma_desc(0, p.b_sub_bytes, p.b_sbo, p.b_layout);
+      const uint64_t a_adv = (uint64_t)((2u * p.a_sbo) >> 4), b_adv = (uint64_t)((2u * p.b_sbo) >> 4);
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(bfull(bs), bph);
         tc_fence_after();
-        const uint64_t bdesc = umma_desc(b_base + bs * p.b_stage_bytes, p.b_sub_bytes, p.b_sbo, p.b_layout);
+        const uint64_t bdesc = bdesc_hi | (uint64_t)(((b_base + bs * b_stage_bytes) >> 4) & 0x3FFF);
         for (int g = g_begin; g < g_end; ++g) {
           mbar_wait(afull(s), ph);
           tc_fence_after();
-          const uint64_t adesc = umma_desc(smem_base + s * p.a_stage_bytes, p.a_sub_bytes, p.a_sbo, p.a_layout);
-          const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_begin) * p.Cout);
-          for (int k = 0; k < ksteps; ++k)   // advance 16 voxel rows = 2 swizzle-atom groups = 2*SBO bytes
-            umma_bf16(d_tmem, adesc + (uint64_t)((2u * p.a_sbo * k) >> 4), bdesc + (uint64_t)((2u * p.b_sbo * k) >> 4), idesc,
-                      (c != c_begin) || (k != 0));
-          umma_commit(aempty(s));
-          if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+          if (elect_one_sync()) {
+            const uint64_t adesc = adesc_hi | (uint64_t)(((smem_base + s * a_stage_bytes) >> 4) & 0x3FFF);
+            const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_begin) * Cout);
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k)   // advance 16 voxel rows = 2 swizzle-atom groups = 2*SBO bytes
+              umma_bf16(d_tmem, adesc + a_adv * k, bdesc + b_adv * k, idesc, (c != c_begin) || (k != 0));
+            umma_commit(aempty(s));
+          }
+          __syncwarp();
+          if (++s == a_stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(bempty(bs));
+        if (elect_one_sync()) umma_commit(bempty(bs));
+        __syncwarp();
         if (++bs == 2) { bs = 0; bph ^= 1u; }
       }
-      umma_commit(accfull);
+      if (elect_one_sync()) umma_commit(accfull);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue: accumulators -> fp32 partials =====
@@ -1116,7 +1125,10 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
 static int wgrad_ok(int c) { return c == 16 || c == 32 || (c % 64 == 0 && c >= 64); }
 
 // the N side of the GEMM (dy channels for mode 0, x channels for the transposed conv) must fit one MMA (<= 256)
-static bool wgrad_use_v1() { static const char* e = getenv("HDF_TC_WGRAD_V1"); return e != nullptr; }
+// v2 (taps stacked along N) issues 40 % fewer, larger MMAs but re-loads the fixed operand per pass and replicates it
+// to fill M; both versions turn out to be bound by L2->SMEM bytes (~2.8 clk per 64-byte box row per SM = the chip's
+// ~6.3 TB/s L2 limit; profiles/r1_microbench_conv_v4_wgrad2.txt), where v1 moves fewer bytes -> v1 is the default.
+static bool wgrad_use_v1() { static const char* e = getenv("HDF_TC_WGRAD_V2"); return e == nullptr; }
 int hdf_tc_wgrad_supported(int mode, int Cin, int Cout) {
   if (mode != 0 && mode != 1) return 0;
   if (!wgrad_use_v1()) return wgrad_ok(Cin) && wgrad_ok(Cout);
