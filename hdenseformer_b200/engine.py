@@ -85,8 +85,8 @@ class Engine:
         self._side = {}
         self._keep_alive = None
 
-    def _side_stream(self, dev):
-        key = dev.index if dev.index is not None else torch.cuda.current_device()
+    def _side_stream(self, dev, idx=0):
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), idx)
         if key not in self._side:
             self._side[key] = torch.cuda.Stream(device=dev)
         return self._side[key]
@@ -330,9 +330,16 @@ class Engine:
         attnall = empty((B, *d16, E * M))
         c.tr = []
         p = DROP_P if training else 0.0
+        mod_streams = []
         for i in range(M):
             pre = f"attns.{i}."
             tr = dict(blocks=[])
+            # modality branches are independent: branch i > 0 gets its own stream (forked from / joined into branch 0)
+            ms = self._side_stream(dev, i) if (side is not None and i > 0) else None
+            if ms is not None:
+                ms.wait_stream(side)
+                mod_ctx = torch.cuda.stream(ms)
+                mod_ctx.__enter__()
             F = empty((R, FW), torch.float32)
             tr["pe_id"] = ids()
             ops.patch_embed_fwd(x, i, P[pre + "patch_embeddings.weight"], P[pre + "patch_embeddings.bias"],
@@ -358,6 +365,11 @@ class Engine:
                 tok = F[:, :E]
             ops.cast_from_f32(tok, attnall.view(R, E * M)[:, i * E:(i + 1) * E])
             c.tr.append(tr)
+            if ms is not None:
+                mod_ctx.__exit__(None, None, None)
+                mod_streams.append(ms)
+        for ms in mod_streams:
+            side.wait_stream(ms)
         c.attnall = attnall
 
         # ---------------- up-sampling path of the transformer features (UpConv x4)
@@ -514,9 +526,15 @@ class Engine:
         # ---- transformer branches
         R = B * cfg.ntok
         p = DROP_P if c.training else 0.0
+        mod_streams = []
         for i in reversed(range(cfg.M)):
             pre = f"attns.{i}."
             tr = c.tr[i]
+            ms = self._side_stream(dev, i) if (side is not None and i > 0) else None
+            if ms is not None:
+                ms.wait_stream(side)
+                mod_ctx = torch.cuda.stream(ms)
+                mod_ctx.__enter__()
             dtok = empty((R, E), torch.float32)
             ops.cast_to_f32(dattnall.view(R, E * cfg.M)[:, i * E:(i + 1) * E], dtok)
             for b in reversed(range(cfg.nblocks)):
@@ -535,6 +553,11 @@ class Engine:
             ops.patch_embed_wgrad(c.x, i, dpe, G[pre + "patch_embeddings.weight"])
             if side is None:
                 notify([k for k in G if k.startswith(pre)][-1])
+            if ms is not None:
+                mod_ctx.__exit__(None, None, None)
+                mod_streams.append(ms)
+        for ms in mod_streams:
+            side.wait_stream(ms)
         branch_ctx.__exit__(None, None, None)
         if side is not None:
             main_stream.wait_stream(side)       # join; the remaining gradient buckets are released together

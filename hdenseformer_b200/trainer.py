@@ -44,9 +44,50 @@ def shard_patches(patches: List[Tuple[int, int, int]], rank: int, world: int) ->
     return patches[rank::world]
 
 
+class _GraphedForward:
+    """Eval forward of one fixed-shape patch captured in a CUDA graph (static input / output buffers)."""
+
+    def __init__(self, net, shape, use_bf16):
+        dev = next(net.parameters()).device
+        self.net, self.use_bf16 = net, use_bf16
+        self.x = torch.zeros(shape, dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+
+    def _run(self):
+        if self.use_bf16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.net(self.x)[0]
+        return self.net(self.x)[0]
+
+    def __call__(self, data):
+        self.x.copy_(data, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
+_FWD_CACHE = {}
+
+
+def _graphed_forward(net, shape, use_bf16):
+    # the graph bakes in parameter addresses, not values: it stays valid across optimizer steps / load_state_dict
+    key = (id(net), tuple(shape), bool(use_bf16), tuple(p.data_ptr() for p in list(net.parameters())[:4]))
+    if key not in _FWD_CACHE:
+        _FWD_CACHE[key] = _GraphedForward(net, shape, use_bf16)
+    return _FWD_CACHE[key]
+
+
 @torch.no_grad()
 def inference_slidingwindow(net, image, n_cls: int, patch_size: Sequence[int], step_size: Sequence[int],
-                            use_bf16: bool = False, group=None, return_prob: bool = False):
+                            use_bf16: bool = False, group=None, return_prob: bool = False, use_graph: bool = False):
     """Sliding-window inference of one volume `image` [M, X, Y, Z] (numpy or tensor, host or device).
 
     Every rank of `group` (or the single process) evaluates its share of the patches and accumulates
@@ -73,9 +114,12 @@ def inference_slidingwindow(net, image, n_cls: int, patch_size: Sequence[int], s
     px, py, pz = patch_size
     if image.device != dev and not image.is_pinned():
         image = image.pin_memory() if torch.cuda.is_available() else image
+    fwd = _graphed_forward(net, (1, M, px, py, pz), use_bf16) if use_graph else None
     for (x, y, z) in mine:
         data = image[None, :, x:x + px, y:y + py, z:z + pz].to(dev, non_blocking=True).contiguous()
-        if use_bf16:
+        if fwd is not None:
+            logits = fwd(data)
+        elif use_bf16:
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 logits = net(data)[0]
         else:
@@ -138,6 +182,7 @@ class GraphedTrainStep:
     def __init__(self, net, criterion, optimizer, example_data: torch.Tensor, example_target: torch.Tensor,
                  use_bf16: bool = True, warmup: int = 3):
         self.net, self.criterion, self.optimizer, self.use_bf16 = net, criterion, optimizer, use_bf16
+        self._copy_stream, self._staged = None, None
         dev = next(net.parameters()).device
         self.x = torch.empty(example_data.shape, dtype=torch.float32, device=dev)
         self.t = torch.empty(example_target.shape, dtype=torch.float32, device=dev)
@@ -167,10 +212,31 @@ class GraphedTrainStep:
         return loss
 
     def step(self, data: torch.Tensor, target: torch.Tensor):
-        self.x.copy_(data, non_blocking=True)
-        self.t.copy_(target, non_blocking=True)
+        if self._staged is not None and self._staged[0] is data and self._staged[1] is target:
+            torch.cuda.current_stream().wait_event(self._staged[2])     # H2D of this batch was prefetched
+            self.x.copy_(self._sx)
+            self.t.copy_(self._st)
+            self._staged = None
+        else:
+            self.x.copy_(data, non_blocking=True)
+            self.t.copy_(target, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+    def prefetch(self, data: torch.Tensor, target: torch.Tensor):
+        """Start the host->device copy of the NEXT step's (pinned) batch on a copy stream so that it overlaps the
+        current step's kernels; `step(data, target)` with the same tensors then only does a device-side copy."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.x.device)
+            self._sx, self._st = torch.empty_like(self.x), torch.empty_like(self.t)
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream())     # staging buffers are free once the previous step consumed them
+        with torch.cuda.stream(cs):
+            self._sx.copy_(data, non_blocking=True)
+            self._st.copy_(target, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._staged = (data, target, ev)
 
 
 class GradBucketer:

@@ -23,14 +23,14 @@ net = net.to(dev).eval()
 vol = O.synth_petct(1, (224, 224, 224), seed=5)[0].pin_memory()
 reps = 3
 for _ in range(2):
-    mask16 = T.inference_slidingwindow(net, vol, 2, size, (72, 72, 72), use_bf16=True)
+    mask16 = T.inference_slidingwindow(net, vol, 2, size, (72, 72, 72), use_bf16=True, use_graph=True)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
-    mask16 = T.inference_slidingwindow(net, vol, 2, size, (72, 72, 72), use_bf16=True)
+    mask16 = T.inference_slidingwindow(net, vol, 2, size, (72, 72, 72), use_bf16=True, use_graph=True)
 e1.record()
 torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
