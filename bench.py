@@ -259,8 +259,12 @@ def main():
         kms = timed(lambda i: ops.tc_conv3d_fwd(xin, wp, None, yout), reps) / reps
         flops = 2.0 * a.batch * D * H * W * 27 * 64 * 32
         ach = flops / (kms / 1e3) / 1e12
+        # DRAM bytes per launch of this kernel from `ncu --set full` (profiles/r1_ncu_conv_fwd_b11r_final.txt:
+        # dram__bytes_read.sum 764.6 MB + dram__bytes_write.sum 365.8 MB; algorithmic 764.4 + 382.2 MB), same shape only
+        traffic = 1.1304e9 if (a.batch == 2 and size == (144, 144, 144)) else None
         roof = {"bound": "tensor", "kernel": "tc_conv_fwd_kernel (block_1_1_right: 64->32 @ full res)", "achieved": ach,
-                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
+                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
+                "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_flop_per_launch": flops,
                 "peak_source": pk["src"] + " burst (kernel timed alone)", "ms_per_launch": kms,
                 "step_frac_of_sustained_peak": (gf_step * value / 1e3) / pk["tf_sustained"]}
         del xin, yout
