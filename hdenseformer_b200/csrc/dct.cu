@@ -348,3 +348,409 @@ int hdf_add_rows_f32(float* dst, long long ldd, const float* src, long long lds,
 }
 
 }  // extern "C"
+
+// =============================================================================================================
+// Fused row-local chain of one DCT inner layer (models/HDenseFormer.py:95-98):
+//     h1 = drop_a(o Wo^T + bo) + h0 ;  h2 = FF(LN2(h1)) + h1 ;  feature = FF(LN2(h2))
+//     FF(x) = drop(W2 drop(gelu(W1 x + b1)) + b2)        (the SAME ff module twice, fresh masks)
+// One block = 32 token rows, 4 threads per row; weights staged (transposed) in shared memory.  Replaces 7 launches
+// in forward and ~35 in backward; weight-gradient contributions are reduced inside the block and written as
+// per-block partials that dct_c_reduce_kernel sums in a fixed order (deterministic).
+// =============================================================================================================
+namespace {
+
+constexpr int FR = 32;      // rows per block
+constexpr int FG = 32;      // growth rate (token width)
+constexpr int FH = 64;      // mlp hidden width
+// per-block weight-gradient partial layout (floats)
+constexpr int P_W2 = 0, P_B2 = P_W2 + FG * FH, P_W1 = P_B2 + FG, P_B1 = P_W1 + FH * FG, P_WO = P_B1 + FH,
+              P_BO = P_WO + FG * FG, P_GM = P_BO + FG, P_BT = P_GM + FG, P_TOTAL = P_BT + FG;
+
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad(float z) {
+  const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * z * z);
+  return cdf + z * pdf;
+}
+// out[j] += sum_k xs[k] * Ws[k*N + sub*(N/4) + j]      (row vector in smem, weights [K][N] in smem)
+template <int K, int N>
+__device__ __forceinline__ void rowmm(const float* xs, const float* Ws, int sub, float* out) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float x = xs[k];
+    const float* w = Ws + k * N + sub * (N / 4);
+#pragma unroll
+    for (int j = 0; j < N / 4; ++j) out[j] = fmaf(x, w[j], out[j]);
+  }
+}
+// sum over the 4 threads that share a row (adjacent lanes)
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+struct DctCParams {
+  // activations (row-major fp32)
+  const float* o; const float* h0;
+  float* h1; float* n2; float* z1; float* f1; float* h2; float* n3; float* z1b; float* g1;
+  float* m2; float* r2; float* m3; float* r3;
+  float* fout; long long ldf;
+  // parameters
+  const float* Wo; const float* bo; const float* gm; const float* bt; const float* W1; const float* b1; const float* W2;
+  const float* b2;
+  int R;
+  float p; const unsigned long long* seed_ptr; unsigned long long seed; unsigned ida, idb, idc, idd, ide;
+};
+
+__global__ void __launch_bounds__(128) dct_c_fwd_kernel(const DctCParams q) {
+  extern __shared__ float sm[];
+  float* WoT = sm;                  // [32][32]   WoT[k][j] = Wo[j][k]
+  float* W1T = WoT + FG * FG;       // [32][64]
+  float* W2T = W1T + FG * FH;       // [64][32]
+  float* xs = W2T + FH * FG;        // [32 rows][64]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FG * FG; i += 128) WoT[(i % FG) * FG + i / FG] = q.Wo[i];
+  for (int i = tid; i < FH * FG; i += 128) W1T[(i % FG) * FH + i / FG] = q.W1[i];   // W1 [64][32]
+  for (int i = tid; i < FG * FH; i += 128) W2T[(i % FH) * FG + i / FH] = q.W2[i];   // W2 [32][64]
+  __syncthreads();
+  const int rl = tid / 4, sub = tid % 4;
+  const long long row = (long long)blockIdx.x * FR + rl;
+  const bool ok = row < q.R;
+  const long long rr = ok ? row : 0;
+  const unsigned long long seed = q.seed + (q.seed_ptr ? *q.seed_ptr : 0ull);
+  float* xr = xs + rl * FH;
+  // ---- h1 = drop_a(o Wo^T + bo) + h0
+#pragma unroll
+  for (int j = 0; j < 8; ++j) xr[sub * 8 + j] = q.o[rr * FG + sub * 8 + j];
+  __syncwarp();
+  float h1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h1[j] = q.bo[sub * 8 + j];
+  rowmm<FG, FG>(xr, WoT, sub, h1);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = sub * 8 + j;
+    h1[j] = h1[j] * hdf_dropout_scale(seed, q.ida, (unsigned long long)rr * FG + c, q.p) + q.h0[rr * FG + c];
+  }
+  float hcur[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hcur[j] = h1[j];
+  for (int pass = 0; pass < 2; ++pass) {
+    // ---- n = LN2(hcur)
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += hcur[j];
+    const float mu = quad_sum(s) * (1.f / FG);
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = hcur[j] - mu; v += d * d; }
+    const float rs = rsqrtf(quad_sum(v) * (1.f / FG) + 1e-5f);
+    float nn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nn[j] = (hcur[j] - mu) * rs * q.gm[sub * 8 + j] + q.bt[sub * 8 + j];
+    float* hsave = pass == 0 ? q.h1 : q.h2;
+    float* nsave = pass == 0 ? q.n2 : q.n3;
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { hsave[row * FG + sub * 8 + j] = hcur[j]; nsave[row * FG + sub * 8 + j] = nn[j]; }
+      if (sub == 0) { (pass == 0 ? q.m2 : q.m3)[row] = mu; (pass == 0 ? q.r2 : q.r3)[row] = rs; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xr[sub * 8 + j] = nn[j];
+    __syncwarp();
+    // ---- z = W1 n + b1 ; f = drop(gelu(z))
+    float z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = q.b1[sub * 16 + j];
+    rowmm<FG, FH>(xr, W1T, sub, z);
+    float* zsave = pass == 0 ? q.z1 : q.z1b;
+    float* fsave = pass == 0 ? q.f1 : q.g1;
+    const unsigned id1 = pass == 0 ? q.idb : q.idd, id2 = pass == 0 ? q.idc : q.ide;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = sub * 16 + j;
+      f[j] = gelu_f(z[j]) * hdf_dropout_scale(seed, id1, (unsigned long long)rr * FH + c, q.p);
+      if (ok) { zsave[row * FH + c] = z[j]; fsave[row * FH + c] = f[j]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) xr[sub * 16 + j] = f[j];
+    __syncwarp();
+    // ---- y = drop(W2 f + b2)
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = q.b2[sub * 8 + j];
+    rowmm<FH, FG>(xr, W2T, sub, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] *= hdf_dropout_scale(seed, id2, (unsigned long long)rr * FG + sub * 8 + j, q.p);
+    if (pass == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hcur[j] = y[j] + h1[j];     // h2 = FF(LN(h1)) + h1
+    } else if (ok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q.fout[row * q.ldf + sub * 8 + j] = y[j];   // appended feature (no residual)
+    }
+    __syncwarp();
+  }
+}
+
+struct DctCBwdParams {
+  const float* dg2; long long ldg;           // grad of the appended feature (slice of dF)
+  const float* o; const float* h1; const float* n2; const float* z1; const float* f1; const float* h2; const float* n3;
+  const float* z1b; const float* g1; const float* m2; const float* r2; const float* m3; const float* r3;
+  const float* Wo; const float* gm; const float* W1; const float* W2;
+  float* d_o; float* dh1;                    // outputs [R,32]
+  float* partial;                            // [gridDim.x][P_TOTAL]
+  int R;
+  float p; const unsigned long long* seed_ptr; unsigned long long seed; unsigned ida, idb, idc, idd, ide;
+};
+
+__global__ void __launch_bounds__(128) dct_c_bwd_kernel(const DctCBwdParams q) {
+  extern __shared__ float sm[];
+  float* Wo = sm;                    // [32][32] natural:  d_o[k] = sum_j dzo[j] Wo[j][k]
+  float* W1 = Wo + FG * FG;          // [64][32] natural:  dn[k]  = sum_j dz[j]  W1[j][k]
+  float* W2 = W1 + FH * FG;          // [32][64] natural:  df[k]  = sum_j dzz[j] W2[j][k]
+  float* xs = W2 + FG * FH;          // [32][64] row scratch
+  float* s_dzz = xs + FR * FH;       // [32][32]   grads wrt pre-dropout FF outputs (2nd use)
+  float* s_dzz2 = s_dzz + FR * FG;   // [32][32]   (1st use)
+  float* s_dz1b = s_dzz2 + FR * FG;  // [32][64]
+  float* s_dz1 = s_dz1b + FR * FH;   // [32][64]
+  float* s_dzo = s_dz1 + FR * FH;    // [32][32]
+  float* s_g1 = s_dzo + FR * FG;     // [32][64]
+  float* s_f1 = s_g1 + FR * FH;      // [32][64]
+  float* s_n3 = s_f1 + FR * FH;      // [32][32]
+  float* s_n2 = s_n3 + FR * FG;      // [32][32]
+  float* s_o = s_n2 + FR * FG;       // [32][32]
+  float* s_dgm = s_o + FR * FG;      // [32][32]  per-row d(gamma) contributions
+  float* s_dbt = s_dgm + FR * FG;    // [32][32]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FG * FG; i += 128) Wo[i] = q.Wo[i];
+  for (int i = tid; i < FH * FG; i += 128) W1[i] = q.W1[i];
+  for (int i = tid; i < FG * FH; i += 128) W2[i] = q.W2[i];
+  const int rl = tid / 4, sub = tid % 4;
+  const long long row = (long long)blockIdx.x * FR + rl;
+  const bool ok = row < q.R;
+  const long long rr = ok ? row : 0;
+  const float live = ok ? 1.f : 0.f;
+  const unsigned long long seed = q.seed + (q.seed_ptr ? *q.seed_ptr : 0ull);
+  // stage the saved activations needed by the weight gradients
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    s_g1[rl * FH + sub * 16 + j] = live * q.g1[rr * FH + sub * 16 + j];
+    s_f1[rl * FH + sub * 16 + j] = live * q.f1[rr * FH + sub * 16 + j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_n3[rl * FG + sub * 8 + j] = live * q.n3[rr * FG + sub * 8 + j];
+    s_n2[rl * FG + sub * 8 + j] = live * q.n2[rr * FG + sub * 8 + j];
+    s_o[rl * FG + sub * 8 + j] = live * q.o[rr * FG + sub * 8 + j];
+  }
+  __syncthreads();
+  float* xr = xs + rl * FH;
+  float dgm_acc[8], dbt_acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dgm_acc[j] = dbt_acc[j] = 0.f;
+  float dh[8];   // running gradient of the residual stream
+  // ======== second FF use (feature branch): dg2 -> dh2
+  float dzz[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = sub * 8 + j;
+    dzz[j] = live * q.dg2[rr * q.ldg + c] * hdf_dropout_scale(seed, q.ide, (unsigned long long)rr * FG + c, q.p);
+    s_dzz[rl * FG + c] = dzz[j];
+    xr[c] = dzz[j];
+  }
+  __syncwarp();
+  for (int pass = 0; pass < 2; ++pass) {
+    // d(hidden) = dzz W2 ; dz = d(hidden) * mask * gelu'(z)
+    float dhid[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dhid[j] = 0.f;
+    rowmm<FG, FH>(xr, W2, sub, dhid);
+    const float* zsv = pass == 0 ? q.z1b : q.z1;
+    const unsigned idh = pass == 0 ? q.idd : q.idb;
+    float* s_dz = pass == 0 ? s_dz1b : s_dz1;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = sub * 16 + j;
+      const float dz = dhid[j] * hdf_dropout_scale(seed, idh, (unsigned long long)rr * FH + c, q.p) * gelu_grad(zsv[rr * FH + c]);
+      s_dz[rl * FH + c] = live * dz;
+      xr[c] = dz;
+    }
+    __syncwarp();
+    // dn = dz W1 ; LayerNorm backward
+    float dn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dn[j] = 0.f;
+    rowmm<FH, FG>(xr, W1, sub, dn);
+    const float* hsv = pass == 0 ? q.h2 : q.h1;
+    const float mu = (pass == 0 ? q.m3 : q.m2)[rr], rs = (pass == 0 ? q.r3 : q.r2)[rr];
+    float xh[8], a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = sub * 8 + j;
+      xh[j] = (hsv[rr * FG + c] - mu) * rs;
+      const float g = dn[j] * q.gm[c];
+      a += g;
+      b += g * xh[j];
+      dgm_acc[j] += live * dn[j] * xh[j];
+      dbt_acc[j] += live * dn[j];
+    }
+    a = quad_sum(a) * (1.f / FG);
+    b = quad_sum(b) * (1.f / FG);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = rs * (dn[j] * q.gm[sub * 8 + j] - a - xh[j] * b);
+      dh[j] = pass == 0 ? v : dh[j] + v;       // pass 0: dh2 (h2 feeds only LN) ; pass 1: dh1 = dh2 + LN-branch
+    }
+    __syncwarp();
+    if (pass == 0) {
+      // first FF use: h2 = drop_c(W2 f1 + b2) + h1
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = sub * 8 + j;
+        const float d2 = dh[j] * hdf_dropout_scale(seed, q.idc, (unsigned long long)rr * FG + c, q.p);
+        s_dzz2[rl * FG + c] = live * d2;
+        xr[c] = d2;
+      }
+      __syncwarp();
+    }
+  }
+  // ======== h1 = drop_a(o Wo^T + bo) + h0
+  float dzo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = sub * 8 + j;
+    dzo[j] = dh[j] * hdf_dropout_scale(seed, q.ida, (unsigned long long)rr * FG + c, q.p);
+    s_dzo[rl * FG + c] = live * dzo[j];
+    xr[c] = dzo[j];
+    s_dgm[rl * FG + c] = dgm_acc[j];
+    s_dbt[rl * FG + c] = dbt_acc[j];
+  }
+  __syncwarp();
+  float d_o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d_o[j] = 0.f;
+  rowmm<FG, FG>(xr, Wo, sub, d_o);
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { q.d_o[row * FG + sub * 8 + j] = d_o[j]; q.dh1[row * FG + sub * 8 + j] = dh[j]; }
+  }
+  __syncthreads();
+  // ======== block-level weight-gradient partials
+  float* part = q.partial + (long long)blockIdx.x * P_TOTAL;
+  for (int i = tid; i < FG * FH; i += 128) {          // dW2[j][k] (W2 is [32][64])
+    const int j = i / FH, k = i % FH;
+    float s = 0.f;
+    for (int r = 0; r < FR; ++r) s += s_dzz[r * FG + j] * s_g1[r * FH + k] + s_dzz2[r * FG + j] * s_f1[r * FH + k];
+    part[P_W2 + i] = s;
+  }
+  for (int i = tid; i < FH * FG; i += 128) {          // dW1[j][k] (W1 is [64][32])
+    const int j = i / FG, k = i % FG;
+    float s = 0.f;
+    for (int r = 0; r < FR; ++r) s += s_dz1b[r * FH + j] * s_n3[r * FG + k] + s_dz1[r * FH + j] * s_n2[r * FG + k];
+    part[P_W1 + i] = s;
+  }
+  for (int i = tid; i < FG * FG; i += 128) {          // dWo[j][k]
+    const int j = i / FG, k = i % FG;
+    float s = 0.f;
+    for (int r = 0; r < FR; ++r) s += s_dzo[r * FG + j] * s_o[r * FG + k];
+    part[P_WO + i] = s;
+  }
+  if (tid < FG) {
+    float sb2 = 0.f, sbo = 0.f, sg = 0.f, sb = 0.f;
+    for (int r = 0; r < FR; ++r) {
+      sb2 += s_dzz[r * FG + tid] + s_dzz2[r * FG + tid];
+      sbo += s_dzo[r * FG + tid];
+      sg += s_dgm[r * FG + tid];
+      sb += s_dbt[r * FG + tid];
+    }
+    part[P_B2 + tid] = sb2; part[P_BO + tid] = sbo; part[P_GM + tid] = sg; part[P_BT + tid] = sb;
+  }
+  if (tid < FH) {
+    float s = 0.f;
+    for (int r = 0; r < FR; ++r) s += s_dz1b[r * FH + tid] + s_dz1[r * FH + tid];
+    part[P_B1 + tid] = s;
+  }
+}
+
+struct DctCGrads { float* w2; float* b2; float* w1; float* b1; float* wo; float* bo; float* gm; float* bt; };
+
+__global__ void dct_c_reduce_kernel(const float* __restrict__ partial, int nblocks, DctCGrads g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P_TOTAL) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * P_TOTAL + i];
+  float* dst;
+  if (i < P_B2) dst = g.w2 + (i - P_W2);
+  else if (i < P_W1) dst = g.b2 + (i - P_B2);
+  else if (i < P_B1) dst = g.w1 + (i - P_W1);
+  else if (i < P_WO) dst = g.b1 + (i - P_B1);
+  else if (i < P_BO) dst = g.wo + (i - P_WO);
+  else if (i < P_GM) dst = g.bo + (i - P_BO);
+  else if (i < P_BT) dst = g.gm + (i - P_GM);
+  else dst = g.bt + (i - P_BT);
+  *dst += s;
+}
+
+constexpr size_t DCT_C_FWD_SMEM = (size_t)(FG * FG + FG * FH + FH * FG + FR * FH) * sizeof(float);
+constexpr size_t DCT_C_BWD_SMEM =
+    (size_t)(FG * FG + FH * FG + FG * FH + FR * FH + 2 * FR * FG + 2 * FR * FH + FR * FG + 2 * FR * FH + 3 * FR * FG + 2 * FR * FG) *
+    sizeof(float);
+
+}  // namespace
+
+extern "C" {
+
+// Fused forward of the post-attention chain of one DCT inner layer.  All row tensors are dense fp32 [R, 32] / [R, 64];
+// fout is the feature slice (stride ldf).  growth_rate 32 / mlp 64 / are the reference's constants.
+int hdf_dct_c_fwd(const float* o, const float* h0, float* h1, float* n2, float* z1, float* f1, float* h2, float* n3, float* z1b,
+                  float* g1, float* m2, float* r2, float* m3, float* r3, float* fout, long long ldf, const float* Wo,
+                  const float* bo, const float* gm, const float* bt, const float* W1, const float* b1, const float* W2,
+                  const float* b2, int R, float p, const unsigned long long* seed_ptr, unsigned long long seed, unsigned ida,
+                  unsigned idb, unsigned idc, unsigned idd, unsigned ide, void* stream) {
+  HDF_REQUIRE(o && h0 && h1 && n2 && z1 && f1 && h2 && n3 && z1b && g1 && m2 && r2 && m3 && r3 && fout && Wo && bo && gm && bt &&
+                  W1 && b1 && W2 && b2 && R > 0, "hdf_dct_c_fwd: null pointer");
+  DctCParams q{o, h0, h1, n2, z1, f1, h2, n3, z1b, g1, m2, r2, m3, r3, fout, ldf, Wo, bo, gm, bt, W1, b1, W2, b2, R, p, seed_ptr,
+               seed, ida, idb, idc, idd, ide};
+  dct_c_fwd_kernel<<<cdiv(R, FR), 128, DCT_C_FWD_SMEM, (cudaStream_t)stream>>>(q);
+  HDF_LAUNCH_CHECK("hdf_dct_c_fwd");
+  return HDF_OK;
+}
+
+size_t hdf_dct_c_bwd_workspace(int R) { return (size_t)cdiv(R, FR) * P_TOTAL * sizeof(float); }
+
+// Fused backward of the same chain: d_o (grad of the attention output) and dh1 (grad of the residual stream entering the
+// layer's attention sub-block) plus += into the eight parameter gradients.
+int hdf_dct_c_bwd(const float* dg2, long long ldg, const float* o, const float* h1, const float* n2, const float* z1,
+                  const float* f1, const float* h2, const float* n3, const float* z1b, const float* g1, const float* m2,
+                  const float* r2, const float* m3, const float* r3, const float* Wo, const float* gm, const float* W1,
+                  const float* W2, float* d_o, float* dh1, float* dW2, float* db2, float* dW1, float* db1, float* dWo, float* dbo,
+                  float* dgm, float* dbt, int R, float p, const unsigned long long* seed_ptr, unsigned long long seed,
+                  unsigned ida, unsigned idb, unsigned idc, unsigned idd, unsigned ide, void* workspace, size_t ws_bytes,
+                  void* stream) {
+  HDF_REQUIRE(dg2 && o && h1 && n2 && z1 && f1 && h2 && n3 && z1b && g1 && m2 && r2 && m3 && r3 && Wo && gm && W1 && W2 && d_o &&
+                  dh1 && dW2 && db2 && dW1 && db1 && dWo && dbo && dgm && dbt && workspace, "hdf_dct_c_bwd: null pointer");
+  HDF_REQUIRE(ws_bytes >= hdf_dct_c_bwd_workspace(R), "hdf_dct_c_bwd: workspace too small");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dct_c_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCT_C_BWD_SMEM);
+    if (e != cudaSuccess) { hdf_set_error("hdf_dct_c_bwd: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
+    configured = true;
+  }
+  const int nb = cdiv(R, FR);
+  DctCBwdParams q{dg2, ldg, o, h1, n2, z1, f1, h2, n3, z1b, g1, m2, r2, m3, r3, Wo, gm, W1, W2, d_o, dh1, (float*)workspace, R, p,
+                  seed_ptr, seed, ida, idb, idc, idd, ide};
+  dct_c_bwd_kernel<<<nb, 128, DCT_C_BWD_SMEM, (cudaStream_t)stream>>>(q);
+  HDF_LAUNCH_CHECK("hdf_dct_c_bwd");
+  DctCGrads g{dW2, db2, dW1, db1, dWo, dbo, dgm, dbt};
+  dct_c_reduce_kernel<<<cdiv(P_TOTAL, 128), 128, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, g);
+  HDF_LAUNCH_CHECK("hdf_dct_c_bwd/reduce");
+  return HDF_OK;
+}
+
+}  // extern "C"

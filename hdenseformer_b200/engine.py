@@ -81,6 +81,7 @@ class Engine:
         self.use_tc = True   # tcgen05 convolution path when available (bf16 only)
         # The transformer branch is ~1100 tiny latency-bound launches; it runs on a second stream next to the big
         # full-resolution convolutions (forward: encoder level 1; backward: the last two encoder blocks).
+        self.fused_dct = True     # fused post-attention chain kernels (csrc/dct.cu) instead of ~40 single-op launches
         self.use_side_stream = True
         self._side = {}
         self._keep_alive = None
@@ -197,27 +198,27 @@ class Engine:
             qkv = torch.empty((R, 3 * GROWTH), dtype=f32, device=dev)
             ops.gemm(n1, P[q + "1.fn.to_qkv.weight"], True, qkv)
             o, lse = ops.attention_fwd(qkv, B, R // B, HEADS, (GROWTH // HEADS) ** -0.5)
+            ida, idb, idc, idd, ide = ids(), ids(), ids(), ids(), ids()
+            if self.fused_dct:
+                sv = ops.dct_c_fwd(o, h0, P, q, F[:, Cl:Cl + GROWTH], p, seed, (ida, idb, idc, idd, ide))
+                layers.append(dict(h0=h0, n1=n1, m1=m1, r1=r1, qkv=qkv, o=o, lse=lse, sv=sv, ids=(ida, idb, idc, idd, ide)))
+                continue
             h1 = torch.empty((R, GROWTH), dtype=f32, device=dev)
-            ida = ids()
             ops.gemm(o, P[q + "1.fn.to_out.0.weight"], True, h1, bias=P[q + "1.fn.to_out.0.bias"], residual=h0, p=p, seed=seed,
                      call_id=ida)
             n2, m2, r2 = ops.layernorm_fwd(h1, P[q + "2.norm.weight"], P[q + "2.norm.bias"])
             z1 = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
             f1 = torch.empty_like(z1)
-            idb = ids()
             ops.gemm(n2, P[q + "2.fn.net.0.weight"], True, f1, bias=P[q + "2.fn.net.0.bias"], pre=z1, act=1, p=p, seed=seed,
                      call_id=idb)
             h2 = torch.empty((R, GROWTH), dtype=f32, device=dev)
-            idc = ids()
             ops.gemm(f1, P[q + "2.fn.net.3.weight"], True, h2, bias=P[q + "2.fn.net.3.bias"], residual=h1, p=p, seed=seed,
                      call_id=idc)
             n3, m3, r3 = ops.layernorm_fwd(h2, P[q + "2.norm.weight"], P[q + "2.norm.bias"])
             z1b = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
             g1 = torch.empty_like(z1b)
-            idd = ids()
             ops.gemm(n3, P[q + "2.fn.net.0.weight"], True, g1, bias=P[q + "2.fn.net.0.bias"], pre=z1b, act=1, p=p, seed=seed,
                      call_id=idd)
-            ide = ids()
             ops.gemm(g1, P[q + "2.fn.net.3.weight"], True, F[:, Cl:Cl + GROWTH], bias=P[q + "2.fn.net.3.bias"], p=p, seed=seed,
                      call_id=ide)
             layers.append(dict(h0=h0, n1=n1, m1=m1, r1=r1, qkv=qkv, o=o, lse=lse, h1=h1, n2=n2, m2=m2, r2=r2, z1=z1, f1=f1,
@@ -229,6 +230,47 @@ class Engine:
                  seed=seed, call_id=idf)
         saved.update(F=F, layers=layers, zo=zo, o1=o1, idf=idf)
         return o1
+
+    def _dct_c_bwd_unfused(self, P, G, q, s, dg2, R, p, seed):
+        """reference composition of the chain backward from single-op kernels (kept for A/B testing)"""
+        dev = dg2.device
+        f32 = torch.float32
+        ida, idb, idc, idd, ide = s["ids"]
+        W1, W2 = P[q + "2.fn.net.0.weight"], P[q + "2.fn.net.3.weight"]
+        # features.append(ff(LN(h2)))
+        dzz = ops.act_dropout_bwd(dg2, None, 0, p, seed, ide)
+        ops.gemm_at_b(dzz, s["g1"], G[q + "2.fn.net.3.weight"])
+        ops.colsum(dzz, G[q + "2.fn.net.3.bias"], accumulate=True)
+        dg1 = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
+        ops.gemm(dzz, W2, False, dg1)
+        dz1b = ops.act_dropout_bwd(dg1, s["z1b"], 1, p, seed, idd)
+        ops.gemm_at_b(dz1b, s["n3"], G[q + "2.fn.net.0.weight"])
+        ops.colsum(dz1b, G[q + "2.fn.net.0.bias"], accumulate=True)
+        dn3 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+        ops.gemm(dz1b, W1, False, dn3)
+        dh = torch.empty((R, GROWTH), dtype=f32, device=dev)      # running grad of the residual stream
+        ops.layernorm_bwd(dn3, s["h2"], s["m3"], s["r3"], P[q + "2.norm.weight"], dh, False, G[q + "2.norm.weight"],
+                          G[q + "2.norm.bias"])
+        # h2 = drop(f1 W2^T + b2) + h1
+        dzz2 = ops.act_dropout_bwd(dh, None, 0, p, seed, idc)
+        ops.gemm_at_b(dzz2, s["f1"], G[q + "2.fn.net.3.weight"])
+        ops.colsum(dzz2, G[q + "2.fn.net.3.bias"], accumulate=True)
+        df1 = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
+        ops.gemm(dzz2, W2, False, df1)
+        dz1 = ops.act_dropout_bwd(df1, s["z1"], 1, p, seed, idb)
+        ops.gemm_at_b(dz1, s["n2"], G[q + "2.fn.net.0.weight"])
+        ops.colsum(dz1, G[q + "2.fn.net.0.bias"], accumulate=True)
+        dn2 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+        ops.gemm(dz1, W1, False, dn2)
+        ops.layernorm_bwd(dn2, s["h1"], s["m2"], s["r2"], P[q + "2.norm.weight"], dh, True, G[q + "2.norm.weight"],
+                          G[q + "2.norm.bias"])
+        # h1 = drop(o Wo^T + bo) + h0
+        dzo_ = ops.act_dropout_bwd(dh, None, 0, p, seed, ida)
+        ops.gemm_at_b(dzo_, s["o"], G[q + "1.fn.to_out.0.weight"])
+        ops.colsum(dzo_, G[q + "1.fn.to_out.0.bias"], accumulate=True)
+        do = torch.empty((R, GROWTH), dtype=f32, device=dev)
+        ops.gemm(dzo_, P[q + "1.fn.to_out.0.weight"], False, do)
+        return do, dh
 
     def _dct_block_bwd(self, P, G, pre, saved, d_o1, R, B, training, seed):
         """d_o1: grad wrt out_layer hidden (after GELU+dropout).  Returns dX = grad wrt block input [R,E] view."""
@@ -248,40 +290,10 @@ class Engine:
             s = saved["layers"][l]
             ida, idb, idc, idd, ide = s["ids"]
             Cl = E + GROWTH * l
-            W1, W2 = P[q + "2.fn.net.0.weight"], P[q + "2.fn.net.3.weight"]
-            # features.append(ff(LN(h2)))
-            dzz = ops.act_dropout_bwd(dF[:, Cl:Cl + GROWTH], None, 0, p, seed, ide)
-            ops.gemm_at_b(dzz, s["g1"], G[q + "2.fn.net.3.weight"])
-            ops.colsum(dzz, G[q + "2.fn.net.3.bias"], accumulate=True)
-            dg1 = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
-            ops.gemm(dzz, W2, False, dg1)
-            dz1b = ops.act_dropout_bwd(dg1, s["z1b"], 1, p, seed, idd)
-            ops.gemm_at_b(dz1b, s["n3"], G[q + "2.fn.net.0.weight"])
-            ops.colsum(dz1b, G[q + "2.fn.net.0.bias"], accumulate=True)
-            dn3 = torch.empty((R, GROWTH), dtype=f32, device=dev)
-            ops.gemm(dz1b, W1, False, dn3)
-            dh = torch.empty((R, GROWTH), dtype=f32, device=dev)      # running grad of the residual stream
-            ops.layernorm_bwd(dn3, s["h2"], s["m3"], s["r3"], P[q + "2.norm.weight"], dh, False, G[q + "2.norm.weight"],
-                              G[q + "2.norm.bias"])
-            # h2 = drop(f1 W2^T + b2) + h1
-            dzz2 = ops.act_dropout_bwd(dh, None, 0, p, seed, idc)
-            ops.gemm_at_b(dzz2, s["f1"], G[q + "2.fn.net.3.weight"])
-            ops.colsum(dzz2, G[q + "2.fn.net.3.bias"], accumulate=True)
-            df1 = torch.empty((R, 2 * GROWTH), dtype=f32, device=dev)
-            ops.gemm(dzz2, W2, False, df1)
-            dz1 = ops.act_dropout_bwd(df1, s["z1"], 1, p, seed, idb)
-            ops.gemm_at_b(dz1, s["n2"], G[q + "2.fn.net.0.weight"])
-            ops.colsum(dz1, G[q + "2.fn.net.0.bias"], accumulate=True)
-            dn2 = torch.empty((R, GROWTH), dtype=f32, device=dev)
-            ops.gemm(dz1, W1, False, dn2)
-            ops.layernorm_bwd(dn2, s["h1"], s["m2"], s["r2"], P[q + "2.norm.weight"], dh, True, G[q + "2.norm.weight"],
-                              G[q + "2.norm.bias"])
-            # h1 = drop(o Wo^T + bo) + h0
-            dzo_ = ops.act_dropout_bwd(dh, None, 0, p, seed, ida)
-            ops.gemm_at_b(dzo_, s["o"], G[q + "1.fn.to_out.0.weight"])
-            ops.colsum(dzo_, G[q + "1.fn.to_out.0.bias"], accumulate=True)
-            do = torch.empty((R, GROWTH), dtype=f32, device=dev)
-            ops.gemm(dzo_, P[q + "1.fn.to_out.0.weight"], False, do)
+            if self.fused_dct:
+                do, dh = ops.dct_c_bwd(dF[:, Cl:Cl + GROWTH], s["o"], s["sv"], P, G, q, p, seed, s["ids"])
+            else:
+                do, dh = self._dct_c_bwd_unfused(P, G, q, s, dF[:, Cl:Cl + GROWTH], R, p, seed)
             dqkv = ops.attention_bwd(s["qkv"], s["o"], do, s["lse"], B, R // B, HEADS, scale)
             ops.gemm_at_b(dqkv, s["n1"], G[q + "1.fn.to_qkv.weight"])
             dn1 = torch.empty((R, GROWTH), dtype=f32, device=dev)

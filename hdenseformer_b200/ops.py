@@ -282,6 +282,44 @@ def add_rows_f32(dst, src, accumulate):
              "add_rows_f32")
 
 
+def dct_c_fwd(o, h0, P, q, fout, p, seed, ids):
+    """fused: h1 = drop(o Wo^T + bo) + h0 ; h2 = FF(LN2(h1)) + h1 ; fout = FF(LN2(h2)).  Returns the saved tensors."""
+    R = o.shape[0]
+    dev = o.device
+    f32 = torch.float32
+    sv = dict(h1=torch.empty((R, 32), dtype=f32, device=dev), n2=torch.empty((R, 32), dtype=f32, device=dev),
+              z1=torch.empty((R, 64), dtype=f32, device=dev), f1=torch.empty((R, 64), dtype=f32, device=dev),
+              h2=torch.empty((R, 32), dtype=f32, device=dev), n3=torch.empty((R, 32), dtype=f32, device=dev),
+              z1b=torch.empty((R, 64), dtype=f32, device=dev), g1=torch.empty((R, 64), dtype=f32, device=dev),
+              m2=torch.empty((R,), dtype=f32, device=dev), r2=torch.empty((R,), dtype=f32, device=dev),
+              m3=torch.empty((R,), dtype=f32, device=dev), r3=torch.empty((R,), dtype=f32, device=dev))
+    sp, so = _seed_args(seed)
+    _C.check(_lib().hdf_dct_c_fwd(_p(o), _p(h0), _p(sv["h1"]), _p(sv["n2"]), _p(sv["z1"]), _p(sv["f1"]), _p(sv["h2"]), _p(sv["n3"]),
+                                  _p(sv["z1b"]), _p(sv["g1"]), _p(sv["m2"]), _p(sv["r2"]), _p(sv["m3"]), _p(sv["r3"]), _p(fout),
+                                  fout.stride(0), _p(P[q + "1.fn.to_out.0.weight"]), _p(P[q + "1.fn.to_out.0.bias"]),
+                                  _p(P[q + "2.norm.weight"]), _p(P[q + "2.norm.bias"]), _p(P[q + "2.fn.net.0.weight"]),
+                                  _p(P[q + "2.fn.net.0.bias"]), _p(P[q + "2.fn.net.3.weight"]), _p(P[q + "2.fn.net.3.bias"]), R,
+                                  float(p), sp, so, *ids, _s()), "dct_c_fwd")
+    return sv
+
+
+def dct_c_bwd(dg2, o, sv, P, G, q, p, seed, ids):
+    """fused backward of dct_c_fwd: returns (d_o, dh1); parameter gradients are accumulated into G."""
+    R = o.shape[0]
+    d_o = torch.empty((R, 32), dtype=torch.float32, device=o.device)
+    dh1 = torch.empty((R, 32), dtype=torch.float32, device=o.device)
+    ws = Workspace.get(_lib().hdf_dct_c_bwd_workspace(R))
+    sp, so = _seed_args(seed)
+    _C.check(_lib().hdf_dct_c_bwd(_p(dg2), dg2.stride(0), _p(o), _p(sv["h1"]), _p(sv["n2"]), _p(sv["z1"]), _p(sv["f1"]), _p(sv["h2"]),
+                                  _p(sv["n3"]), _p(sv["z1b"]), _p(sv["g1"]), _p(sv["m2"]), _p(sv["r2"]), _p(sv["m3"]), _p(sv["r3"]),
+                                  _p(P[q + "1.fn.to_out.0.weight"]), _p(P[q + "2.norm.weight"]), _p(P[q + "2.fn.net.0.weight"]),
+                                  _p(P[q + "2.fn.net.3.weight"]), _p(d_o), _p(dh1), _p(G[q + "2.fn.net.3.weight"]),
+                                  _p(G[q + "2.fn.net.3.bias"]), _p(G[q + "2.fn.net.0.weight"]), _p(G[q + "2.fn.net.0.bias"]),
+                                  _p(G[q + "1.fn.to_out.0.weight"]), _p(G[q + "1.fn.to_out.0.bias"]), _p(G[q + "2.norm.weight"]),
+                                  _p(G[q + "2.norm.bias"]), R, float(p), sp, so, *ids, _p(ws), ws.numel(), _s()), "dct_c_bwd")
+    return d_o, dh1
+
+
 def layernorm_fwd(x, gamma, beta, eps=1e-5):
     M, Cc = x.shape
     out = torch.empty((M, Cc), dtype=torch.float32, device=x.device)

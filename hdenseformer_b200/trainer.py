@@ -11,6 +11,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -196,7 +197,11 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture the main path on a high-priority stream: the kernel nodes inherit it, so the block scheduler
+        # places the big persistent convolution CTAs ahead of the transformer branch's small kernels (which are
+        # captured from default-priority side streams) whenever both are pending
+        hp = torch.cuda.Stream(device=dev, priority=-1) if os.environ.get("HDF_NO_PRIORITY") is None else None
+        with torch.cuda.graph(self.graph, stream=hp):
             self.loss = self._eager()
 
     def _eager(self):

@@ -101,6 +101,22 @@ int hdf_attention_fwd(const float* qkv, long long ld, float* o, long long ldo, f
 int hdf_attention_bwd(const float* qkv, long long ld, const float* o, long long ldo, const float* dout, long long lddo,
                       const float* lse, float* dqkv, long long ldg, int B, int N, int H, float scale, void* stream);
 
+/* fused row-local chain of one DCT inner layer (models/HDenseFormer.py:95-98): attention out-projection + dropout +
+ * residual, then the shared feed-forward applied twice (LN -> Linear -> GELU -> Dropout -> Linear -> Dropout) */
+int hdf_dct_c_fwd(const float* o, const float* h0, float* h1, float* n2, float* z1, float* f1, float* h2, float* n3, float* z1b,
+                  float* g1, float* m2, float* r2, float* m3, float* r3, float* fout, long long ldf, const float* Wo,
+                  const float* bo, const float* gm, const float* bt, const float* W1, const float* b1, const float* W2,
+                  const float* b2, int R, float p, const unsigned long long* seed_ptr, unsigned long long seed, unsigned ida,
+                  unsigned idb, unsigned idc, unsigned idd, unsigned ide, void* stream);
+size_t hdf_dct_c_bwd_workspace(int R);
+int hdf_dct_c_bwd(const float* dg2, long long ldg, const float* o, const float* h1, const float* n2, const float* z1,
+                  const float* f1, const float* h2, const float* n3, const float* z1b, const float* g1, const float* m2,
+                  const float* r2, const float* m3, const float* r3, const float* Wo, const float* gm, const float* W1,
+                  const float* W2, float* d_o, float* dh1, float* dW2, float* db2, float* dW1, float* db1, float* dWo, float* dbo,
+                  float* dgm, float* dbt, int R, float p, const unsigned long long* seed_ptr, unsigned long long seed,
+                  unsigned ida, unsigned idb, unsigned idc, unsigned idd, unsigned ide, void* workspace, size_t ws_bytes,
+                  void* stream);
+
 /* ---- InstanceNorm3d (+affine) + ReLU (+ residual add) (BasicConv3d / UpConv: models/HDenseFormer.py:152-158,
  *      168-169; the "+ at3" adds at :238-244) ---- */
 size_t hdf_reduce_workspace(int N, long long V, int C);

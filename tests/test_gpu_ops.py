@@ -262,3 +262,50 @@ def test_patch_embed_fwd_wgrad():
     dpos = torch.zeros_like(pos)
     ops.posemb_grad(g, dpos, B, ntok, E)
     assert rel(dpos, g.view(B, ntok, E).sum(0, keepdim=True)) < 1e-5
+
+
+def test_fused_dct_chain_matches_unfused_composition():
+    """hdf_dct_c_fwd / hdf_dct_c_bwd (one kernel each) against the same chain composed of single-op kernels, with
+    dropout ON (same counter-based masks on both sides) and a ragged row count."""
+    from hdenseformer_b200.engine import Config, Engine
+    torch.manual_seed(5)
+    R, E = 2 * 27 + 5, 64
+    q = "l."
+    names = {"1.fn.to_out.0.weight": (32, 32), "1.fn.to_out.0.bias": (32,), "2.norm.weight": (32,), "2.norm.bias": (32,),
+             "2.fn.net.0.weight": (64, 32), "2.fn.net.0.bias": (64,), "2.fn.net.3.weight": (32, 64), "2.fn.net.3.bias": (32,)}
+    P = {q + k: (torch.randn(s, device=DEV) * (0.2 if len(s) > 1 else 0.1) + (1.0 if k.endswith("norm.weight") else 0.0))
+         for k, s in names.items()}
+    o, h0 = torch.randn(R, 32, device=DEV), torch.randn(R, 32, device=DEV)
+    ids = (3, 4, 5, 6, 7)
+    seed = torch.tensor([987654321], dtype=torch.int64, device=DEV)
+    F1 = torch.zeros(R, 96, device=DEV)
+    sv = ops.dct_c_fwd(o, h0, P, q, F1[:, 32:64], 0.5, seed, ids)
+    # unfused forward with the same ids
+    pdrop = 0.5
+    h1 = torch.empty(R, 32, device=DEV)
+    ops.gemm(o, P[q + "1.fn.to_out.0.weight"], True, h1, bias=P[q + "1.fn.to_out.0.bias"], residual=h0, p=pdrop, seed=seed, call_id=ids[0])
+    n2, m2, r2 = ops.layernorm_fwd(h1, P[q + "2.norm.weight"], P[q + "2.norm.bias"])
+    z1, f1 = torch.empty(R, 64, device=DEV), torch.empty(R, 64, device=DEV)
+    ops.gemm(n2, P[q + "2.fn.net.0.weight"], True, f1, bias=P[q + "2.fn.net.0.bias"], pre=z1, act=1, p=pdrop, seed=seed, call_id=ids[1])
+    h2 = torch.empty(R, 32, device=DEV)
+    ops.gemm(f1, P[q + "2.fn.net.3.weight"], True, h2, bias=P[q + "2.fn.net.3.bias"], residual=h1, p=pdrop, seed=seed, call_id=ids[2])
+    n3, m3, r3 = ops.layernorm_fwd(h2, P[q + "2.norm.weight"], P[q + "2.norm.bias"])
+    z1b, g1 = torch.empty(R, 64, device=DEV), torch.empty(R, 64, device=DEV)
+    ops.gemm(n3, P[q + "2.fn.net.0.weight"], True, g1, bias=P[q + "2.fn.net.0.bias"], pre=z1b, act=1, p=pdrop, seed=seed, call_id=ids[3])
+    F2 = torch.zeros(R, 96, device=DEV)
+    ops.gemm(g1, P[q + "2.fn.net.3.weight"], True, F2[:, 32:64], bias=P[q + "2.fn.net.3.bias"], p=pdrop, seed=seed, call_id=ids[4])
+    for a, b in ((sv["h1"], h1), (sv["n2"], n2), (sv["z1"], z1), (sv["f1"], f1), (sv["h2"], h2), (sv["n3"], n3), (sv["z1b"], z1b),
+                 (sv["g1"], g1), (F1, F2)):
+        assert rel(a, b) < 1e-5
+    assert (F1[:, :32].abs().max() + F1[:, 64:].abs().max()).item() == 0
+    # backward
+    dF = torch.randn(R, 96, device=DEV)
+    Gf = {k: torch.zeros_like(v) for k, v in P.items()}
+    Gu = {k: torch.zeros_like(v) for k, v in P.items()}
+    do_f, dh_f = ops.dct_c_bwd(dF[:, 32:64], o, sv, P, Gf, q, pdrop, seed, ids)
+    eng = Engine(Config(2, 2, 16, (32, 32, 32), 4))
+    s = dict(o=o, h1=h1, n2=n2, m2=m2, r2=r2, z1=z1, f1=f1, h2=h2, n3=n3, m3=m3, r3=r3, z1b=z1b, g1=g1, ids=ids)
+    do_u, dh_u = eng._dct_c_bwd_unfused(P, Gu, q, s, dF[:, 32:64], R, pdrop, seed)
+    assert rel(do_f, do_u) < 1e-4 and rel(dh_f, dh_u) < 1e-4
+    for k in P:
+        assert rel(Gf[k], Gu[k]) < 1e-4, k
