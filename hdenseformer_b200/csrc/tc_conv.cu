@@ -1053,7 +1053,10 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
   }
   const uint32_t a_region_h = (p.a_bytes + 1023u) & ~1023u;
   p.stage_bytes = a_region_h + (p.b_resident ? 0u : p.b_region);
-  const size_t ring_budget = 200 * 1024 - (p.b_resident ? bres_bytes : 0);
+  // total dynamic smem target per CTA (KB): smaller values leave room for the transformer branch's small kernels to
+  // co-reside with the persistent conv CTAs on the same SM
+  static const int smem_kb = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
+  const size_t ring_budget = (size_t)smem_kb * 1024 - (p.b_resident ? bres_bytes : 0);
   p.stages = (int)(ring_budget / p.stage_bytes);
   if (p.stages > 12) p.stages = 12;
   if (p.stages < 2) { hdf_set_error("hdf_tc_conv3d_fwd: stage too large"); return HDF_ERR_UNSUPPORTED; }
@@ -1163,7 +1166,8 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   p.a_stage_bytes = p.a_sub_bytes * p.SPG;          // = KV*256 bytes, multiple of 1024
   p.b_sub_bytes = (uint32_t)p.KV * p.CWn * 2;
   p.b_stage_bytes = (p.b_sub_bytes * p.nsub_b + 1023u) & ~1023u;
-  p.a_stages = (int)((200u * 1024u - 2u * p.b_stage_bytes) / p.a_stage_bytes);
+  static const int smem_kb = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
+  p.a_stages = (int)(((unsigned)smem_kb * 1024u - 2u * p.b_stage_bytes) / p.a_stage_bytes);
   if (p.a_stages > 6) p.a_stages = 6;
   if (p.a_stages < 2) p.a_stages = 2;
   const int ia = p.CW * 2, ib = p.CWn * 2;

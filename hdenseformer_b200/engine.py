@@ -9,6 +9,7 @@ recomputed from a counter-based RNG instead of being stored.
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -81,10 +82,16 @@ class Engine:
         self.use_tc = True   # tcgen05 convolution path when available (bf16 only)
         # The transformer branch is ~1100 tiny latency-bound launches; it runs on a second stream next to the big
         # full-resolution convolutions (forward: encoder level 1; backward: the last two encoder blocks).
+        # Weight-gradient kernels are off the dependency chain of backward.  They are queued and launched on the main
+        # stream AFTER the point where the transformer branch's backward forks onto the side streams, so that ~9 ms of
+        # tensor-core work is available to overlap the branch's long chain of small, latency-bound kernels.
+        self.defer_wgrad = os.environ.get("HDF_NO_DEFER_WGRAD") is None
+        self._deferred = []
         self.fused_dct = True     # fused post-attention chain kernels (csrc/dct.cu) instead of ~40 single-op launches
-        self.use_side_stream = True
+        self.use_side_stream = os.environ.get("HDF_NO_SIDE_STREAM") is None
         self._side = {}
         self._keep_alive = None
+        self._defer_open = False
 
     def _side_stream(self, dev, idx=0):
         key = (dev.index if dev.index is not None else torch.cuda.current_device(), idx)
@@ -171,7 +178,10 @@ class Engine:
         b = P[f"{name}.norm.bias"] if affine else None
         dy = ops.instnorm_bwd(dout, y, mean, rstd, g, b, G[f"{name}.norm.weight"] if affine else None,
                               G[f"{name}.norm.bias"] if affine else None, relu=True)
-        self._conv_wgrad(x, dy, G[wkey])
+        if self.defer_wgrad and self._defer_open:
+            self._deferred.append((x, dy, G[wkey], 0))
+        else:
+            self._conv_wgrad(x, dy, G[wkey])
         if bias:
             ops.colsum(dy, G[f"{name}.double_conv.0.bias"])
         dx = None
@@ -467,11 +477,16 @@ class Engine:
             """du: grad of the transposed-conv output (a channel-slice view); returns fresh grad wrt its input"""
             da = empty(a_in.shape)
             self._conv_dgrad(du, P[name + ".weight"], da, mode=1)
-            self._conv_wgrad(a_in, du, G[name + ".weight"], mode=1)
+            if self.defer_wgrad and self._defer_open:
+                self._deferred.append((a_in, du, G[name + ".weight"], 1))
+            else:
+                self._conv_wgrad(a_in, du, G[name + ".weight"], mode=1)
             ops.colsum(du, G[name + ".bias"])
             return da
 
         D, H, W = cfg.image_size
+        self._deferred = []
+        self._defer_open = self.use_side_stream and self.defer_wgrad   # only useful with a side branch to overlap
         # ---- level 0 (full resolution)
         dA = empty(c.a12.shape)
         head_bwd("conv1x1", gout(0, (B, cfg.n_cls, D, H, W)), c.a12, dA, False)
@@ -479,19 +494,22 @@ class Engine:
         dcat1 = self._cnr_bwd(c, "block_1_1_right", dA, P, G)
         dA = convt_bwd("upconv_1", dcat1[..., :nf], c.a22)
         head_bwd("conv1x1_d1", gout(1, (B, cfg.n_cls, D // 2, H // 2, W // 2)), c.a22, dA, True)
-        notify("conv1x1_d1.bias")
+        if not self._defer_open:
+            notify("conv1x1_d1.bias")
         # ---- level 1
         dA = self._cnr_bwd(c, "block_2_2_right", dA, P, G)
         dcat2 = self._cnr_bwd(c, "block_2_1_right", dA, P, G)
         dA = convt_bwd("upconv_2", dcat2[..., :2 * nf], c.a32)
         head_bwd("conv1x1_d2", gout(2, (B, cfg.n_cls, D // 4, H // 4, W // 4)), c.a32, dA, True)
-        notify("conv1x1_d2.bias")
+        if not self._defer_open:
+            notify("conv1x1_d2.bias")
         # ---- level 2
         dA = self._cnr_bwd(c, "block_3_2_right", dA, P, G)
         dcat3 = self._cnr_bwd(c, "block_3_1_right", dA, P, G)
         dx4 = convt_bwd("upconv_3", dcat3[..., :4 * nf], c.x4)
         head_bwd("conv1x1_d3", gout(3, (B, cfg.n_cls, D // 8, H // 8, W // 8)), c.x4, dx4, True)
-        notify("conv1x1_d3.bias")
+        if not self._defer_open:
+            notify("conv1x1_d3.bias")
         # ---- bottleneck + encoder (dx4 is also the gradient of attnout through the residual add)
         dA = self._cnr_bwd(c, "block_4_2_left", dx4, P, G)
         dp3 = self._cnr_bwd(c, "block_4_1_left", dA, P, G)
@@ -501,7 +519,8 @@ class Engine:
         dp2 = self._cnr_bwd(c, "block_3_1_left", dA, P, G)
         dds1 = dcat2[..., 2 * nf:]
         ops.maxpool2_bwd(c.cat2[..., 2 * nf:], dp2, dds1, True)
-        notify("block_3_1_left.norm.bias")
+        if not self._defer_open:
+            notify("block_3_1_left.norm.bias")
         dA = self._cnr_bwd(c, "block_2_2_left", dds1, P, G)
         dp1 = self._cnr_bwd(c, "block_2_1_left", dA, P, G)
         dds0 = dcat1[..., nf:]
@@ -510,8 +529,12 @@ class Engine:
         side = self._side_stream(dev) if self.use_side_stream else None
         if side is not None:
             side.wait_stream(main_stream)       # fork: the up path + transformer backward only need dds0/dds1/dds2/dx4
+        self._defer_open = False                # from here on the main stream is the overlap window
         dA = self._cnr_bwd(c, "block_1_2_left", dds0, P, G)
         self._cnr_bwd(c, "block_1_1_left", dA, P, G, need_dx=False)
+        for (wx, wdy, wg, wmode) in self._deferred:
+            self._conv_wgrad(wx, wdy, wg, mode=wmode)
+        self._deferred = []
         if side is None:
             notify("block_1_1_left.norm.bias")
         branch_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
