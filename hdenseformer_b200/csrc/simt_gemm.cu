@@ -464,6 +464,21 @@ __global__ void reduce_transpose_kernel(const float* __restrict__ part, float* _
   }
 }
 
+// tok[m, e] = (sum_s part[s][m][e] + bias[e] + pos[m % ntok, e]) * dropout
+__global__ void patch_finish_kernel(const float* __restrict__ part, int S, float* __restrict__ tok, long long ld,
+                                    const float* __restrict__ bias, const float* __restrict__ pos, int ntok, int E,
+                                    long long total, float p, const unsigned long long* seed_ptr, unsigned long long seed,
+                                    unsigned call_id) {
+  if (seed_ptr) seed += *seed_ptr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = i % E;
+    const long long m = i / E;
+    float v = (bias ? bias[e] : 0.f) + pos[(m % ntok) * E + e];
+    for (int z = 0; z < S; ++z) v += part[z * total + i];
+    tok[m * ld + e] = v * hdf_dropout_scale(seed, call_id, (unsigned long long)i, p);
+  }
+}
+
 // tok[m, e] = (tok[m, e] + pos[m % ntok, e]) * dropout
 __global__ void posemb_dropout_kernel(float* __restrict__ tok, long long ld, const float* __restrict__ pos, int ntok, int E,
                                       long long total, float p, const unsigned long long* seed_ptr,
@@ -552,25 +567,33 @@ int hdf_conv3d_wgrad(int dtype, int mode, const void* x, long long ldx, const vo
   return HDF_OK;
 }
 
+size_t hdf_patch_embed_fwd_workspace(int B, int D, int H, int W, int E) {
+  const long long M = (long long)B * (D / 16) * (H / 16) * (W / 16);
+  return (size_t)8 * M * E * sizeof(float);
+}
+
 // tokens[b, n, :] (ld = ldo) = patch_conv(img[b, modality]) + bias + pos[n, :], then dropout
-// img: NCDHW fp32 [B, Mch, D, H, W]; weight [E, 4096] (torch [E,1,16,16,16]); out fp32
+// img: NCDHW fp32 [B, Mch, D, H, W]; weight [E, 4096] (torch [E,1,16,16,16]); out fp32.
+// K = 4096 is split 8 ways (the GEMM has only ~46 output tiles and sits at the head of the transformer branch's
+// dependency chain); the finishing kernel sums the partials in a fixed order and applies bias + pos-emb + dropout.
 int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, int H, int W, const float* weight,
                         const float* bias, const float* pos, float* out, long long ldo, int E, float p,
-                        const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* stream) {
-  HDF_REQUIRE(img && weight && out && (D % 16 == 0) && (H % 16 == 0) && (W % 16 == 0) && (W % 4 == 0),
+                        const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* workspace,
+                        size_t ws_bytes, void* stream) {
+  HDF_REQUIRE(img && weight && out && workspace && (D % 16 == 0) && (H % 16 == 0) && (W % 16 == 0) && (W % 4 == 0),
               "hdf_patch_embed_fwd: bad args (every spatial dim must be a multiple of 16)");
   const int ntok = (D / 16) * (H / 16) * (W / 16);
   const int M = B * ntok;
+  HDF_REQUIRE(ws_bytes >= (size_t)8 * M * E * sizeof(float), "hdf_patch_embed_fwd: workspace too small");
   PatchA al{img + (long long)modality * D * H * W, (long long)Mch * D * H * W, D, H, W, M, nullptr, false};
   ColMajorB bl{weight, 4096, E};
-  // bias + positional embedding: pos is [ntok, E]; fold via residual with row index modulo ntok -> do in two steps:
-  LinearEp ep{out, ldo, bias, nullptr, 0, nullptr, 0, 0.f, seed_ptr, seed, call_id, 0.f};
-  int rc = launch_gemm(al, bl, ep, M, E, 4096, 1, 1, (cudaStream_t)stream, "hdf_patch_embed_fwd");
+  PartialEp ep{(float*)workspace, 1};
+  int rc = launch_gemm(al, bl, ep, M, E, 4096, 1, 8, (cudaStream_t)stream, "hdf_patch_embed_fwd");
   if (rc) return rc;
   const long long total = (long long)M * E;
-  posemb_dropout_kernel<<<min(1024, cdiv(total, 256)), 256, 0, (cudaStream_t)stream>>>(out, ldo, pos, ntok, E, total, p,
-                                                                                       seed_ptr, seed, call_id);
-  HDF_LAUNCH_CHECK("hdf_patch_embed_fwd/posemb");
+  patch_finish_kernel<<<min(1024, cdiv(total, 256)), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, 8, out, ldo, bias,
+                                                                                    pos, ntok, E, total, p, seed_ptr, seed, call_id);
+  HDF_LAUNCH_CHECK("hdf_patch_embed_fwd/finish");
   return HDF_OK;
 }
 

@@ -344,6 +344,10 @@ class Engine:
             side.wait_stream(main_stream)                                   # fork
         branch_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
         branch_ctx.__enter__()
+        fork_ev = None
+        if side is not None:
+            fork_ev = torch.cuda.Event()
+            fork_ev.record(side)             # modality streams fork from HERE, not from the end of modality 0's work
         # ---------------- transformer branches (fp32 tokens), one per modality
         d16 = cfg.tok_grid
         ntok = cfg.ntok
@@ -359,7 +363,7 @@ class Engine:
             # modality branches are independent: branch i > 0 gets its own stream (forked from / joined into branch 0)
             ms = self._side_stream(dev, i) if (side is not None and i > 0) else None
             if ms is not None:
-                ms.wait_stream(side)
+                ms.wait_event(fork_ev)
                 mod_ctx = torch.cuda.stream(ms)
                 mod_ctx.__enter__()
             F = empty((R, FW), torch.float32)
@@ -527,20 +531,10 @@ class Engine:
         ops.maxpool2_bwd(c.cat1[..., nf:], dp1, dds0, True)
         main_stream = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.use_side_stream else None
-        if side is not None:
-            side.wait_stream(main_stream)       # fork: the up path + transformer backward only need dds0/dds1/dds2/dx4
-        self._defer_open = False                # from here on the main stream is the overlap window
-        dA = self._cnr_bwd(c, "block_1_2_left", dds0, P, G)
-        self._cnr_bwd(c, "block_1_1_left", dA, P, G, need_dx=False)
-        for (wx, wdy, wg, wmode) in self._deferred:
-            self._conv_wgrad(wx, wdy, wg, mode=wmode)
-        self._deferred = []
-        if side is None:
-            notify("block_1_1_left.norm.bias")
-        branch_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
-        branch_ctx.__enter__()
 
-        # ---- transformer-feature up path: at3 <- up3 <- at2 <- up2 <- at1 <- up1 <- attnout <- deep_conv <- attnall
+        # ---- transformer-feature up path: at3 <- up3 <- at2 <- up2 <- at1 <- up1 <- attnout <- deep_conv <- attnall.
+        # It is the head of the longest remaining dependency chain (the transformer backward hangs off it), and its
+        # convolutions cannot share SMs with the other persistent conv kernels, so it goes FIRST on the main stream.
         def upconv_bwd(name, dup, extra):
             """dup: grad wrt the upsampled output; extra: additional grad wrt this UpConv's *input* (or None)"""
             xin, y, _, _ = getattr(c, name)
@@ -555,8 +549,23 @@ class Engine:
         dat1 = upconv_bwd("up2", dat2, dds2)
         dattnout = upconv_bwd("up1", dat1, dx4)
         dattnall = upconv_bwd("deep_conv", dattnout, None)
+
+        fork_ev = None
+        if side is not None:
+            side.wait_stream(main_stream)       # fork: the transformer backward (small kernels) runs beside the window below
+            fork_ev = torch.cuda.Event()
+            fork_ev.record(side)
+        # ---- overlap window on the main stream: last two encoder blocks + every deferred weight gradient
+        self._defer_open = False
+        dA = self._cnr_bwd(c, "block_1_2_left", dds0, P, G)
+        self._cnr_bwd(c, "block_1_1_left", dA, P, G, need_dx=False)
+        for (wx, wdy, wg, wmode) in self._deferred:
+            self._conv_wgrad(wx, wdy, wg, mode=wmode)
+        self._deferred = []
         if side is None:
             notify("deep_conv.double_conv.0.bias")
+        branch_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+        branch_ctx.__enter__()
 
         # ---- transformer branches
         R = B * cfg.ntok
@@ -567,7 +576,7 @@ class Engine:
             tr = c.tr[i]
             ms = self._side_stream(dev, i) if (side is not None and i > 0) else None
             if ms is not None:
-                ms.wait_stream(side)
+                ms.wait_event(fork_ev)
                 mod_ctx = torch.cuda.stream(ms)
                 mod_ctx.__enter__()
             dtok = empty((R, E), torch.float32)

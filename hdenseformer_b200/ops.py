@@ -357,8 +357,10 @@ def attention_bwd(qkv, o, dout, lse, B, N, H, scale):
 def patch_embed_fwd(img, modality, weight, bias, pos, out, p, seed, call_id):
     B, Mch, D, H, W = img.shape
     E = weight.shape[0]
+    ws = Workspace.get(_lib().hdf_patch_embed_fwd_workspace(B, D, H, W, E))
     _C.check(_lib().hdf_patch_embed_fwd(_p(img), B, Mch, modality, D, H, W, _p(weight), _p(bias), _p(pos), _p(out),
-                                        out.stride(0), E, float(p), *_seed_args(seed), call_id, _s()), "patch_embed_fwd")
+                                        out.stride(0), E, float(p), *_seed_args(seed), call_id, _p(ws), ws.numel(), _s()),
+             "patch_embed_fwd")
 
 
 def patch_embed_wgrad(img, modality, dtok, dweight, accumulate=False):

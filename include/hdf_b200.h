@@ -63,9 +63,11 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
 
 /* ---- patch embedding (nn.Conv3d k16 s16 + position_embeddings + Dropout: models/HDenseFormer.py:115-119,
  *      133-138).  img is the caller's NCDHW fp32 batch; tokens are [B*ntok, E] fp32 rows (ld = ldo). ---- */
+size_t hdf_patch_embed_fwd_workspace(int B, int D, int H, int W, int E);
 int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, int H, int W, const float* weight,
                         const float* bias, const float* pos, float* out, long long ldo, int E, float p,
-                        const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* stream);
+                        const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* workspace,
+                        size_t ws_bytes, void* stream);
 /* dropout masks are a pure function of (*seed_ptr + seed, call_id, element index): seed_ptr (nullable) is a device
  * counter the host advances once per forward, so captured CUDA graphs draw fresh masks on every replay */
 size_t hdf_patch_embed_wgrad_workspace(int B, int D, int H, int W, int E);

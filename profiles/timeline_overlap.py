@@ -1,0 +1,84 @@
+"""Kernel timeline of one graph-replayed training step via torch.profiler (CUPTI): per-stream busy time, how much of
+the side-stream (transformer branch) work overlaps main-stream kernels, and the gaps of the main stream."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from oracle import hdf_oracle as O
+from hdenseformer_b200 import trainer as T
+from hdenseformer_b200.loss import CEPlusDice, DeepSuperloss
+from hdenseformer_b200.models import HDenseFormer_32
+
+dev = torch.device("cuda", 0); torch.cuda.set_device(0)
+size = (144, 144, 144)
+net = HDenseFormer_32(2, 2, size, 12).to(dev).train()
+crit = DeepSuperloss(CEPlusDice(ignore_index=0))
+opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True, capturable=True)
+x, t = O.synth_petct(2, size, seed=0).to(dev), O.synth_label(2, 2, size, seed=0).to(dev)
+g = T.GraphedTrainStep(net, crit, opt, x, t, use_bf16=True)
+for _ in range(3): g.step(x, t)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    g.step(x, t)
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
+ks = sorted([(e.time_range.start, e.time_range.end, e.name, getattr(e, "cuda_stream", None) if hasattr(e, "cuda_stream") else None) for e in ev])
+print("kernels", len(ks))
+if not ks: sys.exit(0)
+t0 = ks[0][0]; t1 = max(k[1] for k in ks)
+print("span ms", (t1 - t0) / 1e3)
+# union busy time
+busy = 0; cur_s, cur_e = ks[0][0], ks[0][1]
+for s, e, _, _ in ks[1:]:
+    if s > cur_e: busy += cur_e - cur_s; cur_s, cur_e = s, e
+    else: cur_e = max(cur_e, e)
+busy += cur_e - cur_s
+print("union busy ms", busy / 1e3, "sum of durations ms", sum(e - s for s, e, _, _ in ks) / 1e3)
+big = [(s, e, n) for s, e, n, _ in ks if ("tc_conv" in n)]
+small = [(s, e, n) for s, e, n, _ in ks if ("tc_conv" not in n)]
+print("tc_conv kernels", len(big), "sum ms", sum(e - s for s, e, _ in big) / 1e3)
+# how much small-kernel time falls inside some tc_conv kernel interval
+ov = 0
+for s, e, n in small:
+    for bs, be, _ in big:
+        lo, hi = max(s, bs), min(e, be)
+        if hi > lo: ov += hi - lo
+print("non-conv kernel time ms", sum(e - s for s, e, _ in small) / 1e3, "of which overlapping a tc_conv kernel ms", ov / 1e3)
+# conv kernel durations: in-step vs list
+import collections
+d = collections.defaultdict(list)
+for s, e, n in big: d[n[:40]].append((e - s) / 1e3)
+for k, v in d.items(): print(k, "n", len(v), "sum", round(sum(v), 2), "max", round(max(v), 3))
+# biggest gaps where nothing runs
+gaps = []; cur_e = ks[0][1]
+for s, e, n, _ in ks[1:]:
+    if s > cur_e: gaps.append((s - cur_e, (cur_e - t0) / 1e3, n[:50]))
+    cur_e = max(cur_e, e)
+gaps.sort(reverse=True)
+print("idle total ms", sum(g_[0] for g_ in gaps) / 1e3, "largest gaps (us, at ms, next kernel):", [(round(a, 1), round(b, 2), c) for a, b, c in gaps[:8]])
+
+# ---- forward-phase markers (ms from step start)
+def first(name, nth=0):
+    c = [k for k in ks if name in k[2]]
+    return ((c[nth][0] - t0) / 1e3, (c[nth][1] - t0) / 1e3) if len(c) > nth else None
+def last(name):
+    c = [k for k in ks if name in k[2]]
+    return ((c[-1][0] - t0) / 1e3, (c[-1][1] - t0) / 1e3) if c else None
+print("patch-embed gemm (PatchA) first/last:", first("PatchA"), last("PatchA,"))
+af = [k for k in ks if "attn_fwd" in k[2]]
+print("attn_fwd count", len(af), "first start", (af[0][0] - t0) / 1e3, "last end", (af[-1][1] - t0) / 1e3)
+print("dct_c_fwd last end", last("dct_c_fwd"))
+print("upsample2_fwd ends", [round((k[1] - t0) / 1e3, 3) for k in ks if "upsample2_fwd" in k[2]])
+print("maxpool_fwd starts", [round((k[0] - t0) / 1e3, 3) for k in ks if "maxpool_fwd" in k[2]])
+print("first 3 tc_conv_fwd (start,end)", [(round((k[0] - t0) / 1e3, 3), round((k[1] - t0) / 1e3, 3)) for k in ks if "tc_conv_fwd" in k[2]][:8])
+print("loss_reduce first start", first("loss_reduce"))
+print("attn_bwd_dq first/last", first("attn_bwd_dq"), last("attn_bwd_dq"))
+print("last tc_conv_wgrad end", last("tc_conv_wgrad"))
+print("adam start", first("FusedOptimizer"))
+# per-kernel average in-step duration for the token kernels
+agg = collections.defaultdict(lambda: [0, 0.0])
+for s, e, n, _ in ks:
+    key = n.split("(")[0][-60:]
+    agg[key][0] += 1; agg[key][1] += (e - s) / 1e3
+for k, (n, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"{tt:8.2f} ms {n:5d} {1e3*tt/n:8.1f} us  {k}")
