@@ -754,3 +754,263 @@ int hdf_dct_c_bwd(const float* dg2, long long ldg, const float* o, const float* 
 }
 
 }  // extern "C"
+
+// =============================================================================================================
+// Fused head of one DCT inner layer (models/HDenseFormer.py:94-96, :57):
+//     h0 = Linear_l(cat(features)) ;  n1 = LN1(h0) ;  qkv = n1 Wqkv^T
+// and its backward (dn1 = dqkv Wqkv ; dh0 = dh1 + LN1'(dn1) ; dF[:, :Cl] += dh0 Wl ; weight-gradient partials).
+// Same organisation as the dct_c kernels: 32 rows per block, 4 threads per row, weights in shared memory.
+// =============================================================================================================
+namespace {
+
+constexpr int FQ = 96;   // 3 * growth
+
+// out[j] (j < NOUT/4 per thread) with runtime K:  out += xs[0..K) * Ws[k*NOUT + sub*(NOUT/4) + j]
+template <int NOUT>
+__device__ __forceinline__ void rowmm_k(const float* xs, const float* Ws, int K, int sub, float* out) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float x = xs[k];
+    const float* w = Ws + k * NOUT + sub * (NOUT / 4);
+#pragma unroll
+    for (int j = 0; j < NOUT / 4; ++j) out[j] = fmaf(x, w[j], out[j]);
+  }
+}
+
+struct DctAParams {
+  const float* F; long long ldf; int Cl;
+  const float* Wl; const float* bl; const float* gm; const float* bt; const float* Wqkv;
+  float* h0; float* n1; float* m1; float* r1; float* qkv;
+  int R;
+};
+
+__global__ void __launch_bounds__(128) dct_a_fwd_kernel(const DctAParams q) {
+  extern __shared__ float sm[];
+  const int Cl = q.Cl;
+  float* WlT = sm;                    // [Cl][32]
+  float* WqT = WlT + Cl * FG;         // [32][96]
+  float* fs = WqT + FG * FQ;          // [32 rows][Cl]
+  float* xs = fs + FR * Cl;           // [32 rows][32]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FG * Cl; i += 128) WlT[(i % Cl) * FG + i / Cl] = q.Wl[i];     // Wl [32][Cl]
+  for (int i = tid; i < FQ * FG; i += 128) WqT[(i % FG) * FQ + i / FG] = q.Wqkv[i];   // Wqkv [96][32]
+  const long long row0 = (long long)blockIdx.x * FR;
+  for (int i = tid; i < FR * Cl; i += 128) {
+    const int r = i / Cl, k = i % Cl;
+    fs[i] = (row0 + r < q.R) ? q.F[(row0 + r) * q.ldf + k] : 0.f;
+  }
+  __syncthreads();
+  const int rl = tid / 4, sub = tid % 4;
+  const long long row = row0 + rl;
+  const bool ok = row < q.R;
+  float h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = q.bl[sub * 8 + j];
+  rowmm_k<FG>(fs + rl * Cl, WlT, Cl, sub, h);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += h[j];
+  const float mu = quad_sum(s) * (1.f / FG);
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float d = h[j] - mu; v += d * d; }
+  const float rs = rsqrtf(quad_sum(v) * (1.f / FG) + 1e-5f);
+  float nn[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    nn[j] = (h[j] - mu) * rs * q.gm[sub * 8 + j] + q.bt[sub * 8 + j];
+    xs[rl * FG + sub * 8 + j] = nn[j];
+  }
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { q.h0[row * FG + sub * 8 + j] = h[j]; q.n1[row * FG + sub * 8 + j] = nn[j]; }
+    if (sub == 0) { q.m1[row] = mu; q.r1[row] = rs; }
+  }
+  __syncwarp();
+  float o[24];
+#pragma unroll
+  for (int j = 0; j < 24; ++j) o[j] = 0.f;
+  rowmm<FG, FQ>(xs + rl * FG, WqT, sub, o);
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < 24; ++j) q.qkv[row * FQ + sub * 24 + j] = o[j];
+  }
+}
+
+struct DctABwdParams {
+  const float* dqkv; const float* dh1; const float* h0; const float* n1; const float* m1; const float* r1;
+  const float* F; long long ldf; int Cl;
+  const float* Wqkv; const float* gm; const float* Wl;
+  float* dF; long long lddf;
+  float* partial;      // [grid][FQ*FG + 2*FG + FG*Cl + FG]
+  int R;
+};
+
+__global__ void __launch_bounds__(128) dct_a_bwd_kernel(const DctABwdParams q) {
+  extern __shared__ float sm[];
+  const int Cl = q.Cl;
+  float* Wq = sm;                      // [96][32] natural
+  float* Wl = Wq + FQ * FG;            // [32][Cl] natural
+  float* s_dq = Wl + FG * Cl;          // [32][96]
+  float* s_n1 = s_dq + FR * FQ;        // [32][32]
+  float* s_dh0 = s_n1 + FR * FG;       // [32][32]
+  float* s_f = s_dh0 + FR * FG;        // [32][Cl]
+  float* s_dgm = s_f + FR * Cl;        // [32][32]
+  float* s_dbt = s_dgm + FR * FG;      // [32][32]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FQ * FG; i += 128) Wq[i] = q.Wqkv[i];
+  for (int i = tid; i < FG * Cl; i += 128) Wl[i] = q.Wl[i];
+  const long long row0 = (long long)blockIdx.x * FR;
+  for (int i = tid; i < FR * Cl; i += 128) {
+    const int r = i / Cl, k = i % Cl;
+    s_f[i] = (row0 + r < q.R) ? q.F[(row0 + r) * q.ldf + k] : 0.f;
+  }
+  for (int i = tid; i < FR * FQ; i += 128) {
+    const int r = i / FQ;
+    s_dq[i] = (row0 + r < q.R) ? q.dqkv[(row0 + r) * FQ + i % FQ] : 0.f;
+  }
+  for (int i = tid; i < FR * FG; i += 128) {
+    const int r = i / FG;
+    s_n1[i] = (row0 + r < q.R) ? q.n1[(row0 + r) * FG + i % FG] : 0.f;
+  }
+  __syncthreads();
+  const int rl = tid / 4, sub = tid % 4;
+  const long long row = row0 + rl;
+  const bool ok = row < q.R;
+  const long long rr = ok ? row : 0;
+  const float live = ok ? 1.f : 0.f;
+  // dn1 = dqkv Wqkv
+  float dn[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dn[j] = 0.f;
+  rowmm<FQ, FG>(s_dq + rl * FQ, Wq, sub, dn);
+  // LayerNorm backward, plus the residual-stream gradient coming from the layer's tail
+  const float mu = q.m1[rr], rs = q.r1[rr];
+  float xh[8], a = 0.f, b = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = sub * 8 + j;
+    xh[j] = (q.h0[rr * FG + c] - mu) * rs;
+    const float g = dn[j] * q.gm[c];
+    a += g;
+    b += g * xh[j];
+    s_dgm[rl * FG + c] = live * dn[j] * xh[j];
+    s_dbt[rl * FG + c] = live * dn[j];
+  }
+  a = quad_sum(a) * (1.f / FG);
+  b = quad_sum(b) * (1.f / FG);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = sub * 8 + j;
+    const float dh0 = live * (q.dh1[rr * FG + c] + rs * (dn[j] * q.gm[c] - a - xh[j] * b));
+    s_dh0[rl * FG + c] = dh0;
+  }
+  __syncwarp();
+  // dF[row, :Cl] += dh0 Wl    (each of the 4 threads of the row owns Cl/4 consecutive columns, 8 at a time)
+  if (ok) {
+    const int per = Cl / 4;
+    for (int c0 = 0; c0 < per; c0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < FG; ++k) {
+        const float x = s_dh0[rl * FG + k];
+        const float* w = Wl + k * Cl + sub * per + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, w[j], acc[j]);
+      }
+      float* dst = q.dF + row * q.lddf + sub * per + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] += acc[j];
+    }
+  }
+  __syncthreads();
+  // block-level weight-gradient partials: [dWqkv 96x32][dgm 32][dbt 32][dWl 32xCl][dbl 32]
+  float* part = q.partial + (long long)blockIdx.x * (FQ * FG + 2 * FG + FG * Cl + FG);
+  for (int i = tid; i < FQ * FG; i += 128) {
+    const int j = i / FG, k = i % FG;
+    float s = 0.f;
+    for (int r = 0; r < FR; ++r) s += s_dq[r * FQ + j] * s_n1[r * FG + k];
+    part[i] = s;
+  }
+  if (tid < FG) {
+    float sg = 0.f, sb = 0.f, sl = 0.f;
+    for (int r = 0; r < FR; ++r) { sg += s_dgm[r * FG + tid]; sb += s_dbt[r * FG + tid]; sl += s_dh0[r * FG + tid]; }
+    part[FQ * FG + tid] = sg;
+    part[FQ * FG + FG + tid] = sb;
+    part[FQ * FG + 2 * FG + FG * Cl + tid] = sl;
+  }
+  for (int i = tid; i < FG * Cl; i += 128) {
+    const int j = i / Cl, k = i % Cl;
+    float s = 0.f;
+    for (int r = 0; r < FR; ++r) s += s_dh0[r * FG + j] * s_f[r * Cl + k];
+    part[FQ * FG + 2 * FG + i] = s;
+  }
+}
+
+__global__ void dct_a_reduce_kernel(const float* __restrict__ partial, int nblocks, int Cl, float* dWqkv, float* dgm, float* dbt,
+                                    float* dWl, float* dbl) {
+  const int total = FQ * FG + 2 * FG + FG * Cl + FG;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(long long)b * total + i];
+  float* dst;
+  if (i < FQ * FG) dst = dWqkv + i;
+  else if (i < FQ * FG + FG) dst = dgm + (i - FQ * FG);
+  else if (i < FQ * FG + 2 * FG) dst = dbt + (i - FQ * FG - FG);
+  else if (i < FQ * FG + 2 * FG + FG * Cl) dst = dWl + (i - FQ * FG - 2 * FG);
+  else dst = dbl + (i - FQ * FG - 2 * FG - FG * Cl);
+  *dst += s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hdf_dct_a_fwd(const float* F, long long ldf, int Cl, const float* Wl, const float* bl, const float* gm, const float* bt,
+                  const float* Wqkv, float* h0, float* n1, float* m1, float* r1, float* qkv, int R, void* stream) {
+  HDF_REQUIRE(F && Wl && bl && gm && bt && Wqkv && h0 && n1 && m1 && r1 && qkv && R > 0 && Cl > 0 && Cl % 32 == 0 && Cl <= 512,
+              "hdf_dct_a_fwd: bad args (Cl must be a multiple of 32, <= 512)");
+  const size_t smem = (size_t)(Cl * FG + FG * FQ + FR * Cl + FR * FG) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(dct_a_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { hdf_set_error("hdf_dct_a_fwd: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
+    configured = 200 * 1024;
+  }
+  DctAParams q{F, ldf, Cl, Wl, bl, gm, bt, Wqkv, h0, n1, m1, r1, qkv, R};
+  dct_a_fwd_kernel<<<cdiv(R, FR), 128, smem, (cudaStream_t)stream>>>(q);
+  HDF_LAUNCH_CHECK("hdf_dct_a_fwd");
+  return HDF_OK;
+}
+
+size_t hdf_dct_a_bwd_workspace(int R, int Cl) { return (size_t)cdiv(R, FR) * (FQ * FG + 2 * FG + FG * Cl + FG) * sizeof(float); }
+
+int hdf_dct_a_bwd(const float* dqkv, const float* dh1, const float* h0, const float* n1, const float* m1, const float* r1,
+                  const float* F, long long ldf, int Cl, const float* Wqkv, const float* gm, const float* Wl, float* dF,
+                  long long lddf, float* dWqkv, float* dgm, float* dbt, float* dWl, float* dbl, int R, void* workspace,
+                  size_t ws_bytes, void* stream) {
+  HDF_REQUIRE(dqkv && dh1 && h0 && n1 && m1 && r1 && F && Wqkv && gm && Wl && dF && dWqkv && dgm && dbt && dWl && dbl && workspace &&
+                  R > 0 && Cl % 32 == 0 && Cl <= 512, "hdf_dct_a_bwd: bad args");
+  HDF_REQUIRE(ws_bytes >= hdf_dct_a_bwd_workspace(R, Cl), "hdf_dct_a_bwd: workspace too small");
+  const size_t smem = (size_t)(FQ * FG + FG * Cl + FR * FQ + 2 * FR * FG + FR * Cl + 2 * FR * FG) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(dct_a_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { hdf_set_error("hdf_dct_a_bwd: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
+    configured = 200 * 1024;
+  }
+  HDF_REQUIRE(smem <= 200 * 1024, "hdf_dct_a_bwd: Cl=%d needs too much shared memory", Cl);
+  const int nb = cdiv(R, FR);
+  DctABwdParams q{dqkv, dh1, h0, n1, m1, r1, F, ldf, Cl, Wqkv, gm, Wl, dF, lddf, (float*)workspace, R};
+  dct_a_bwd_kernel<<<nb, 128, smem, (cudaStream_t)stream>>>(q);
+  HDF_LAUNCH_CHECK("hdf_dct_a_bwd");
+  const int total = FQ * FG + 2 * FG + FG * Cl + FG;
+  dct_a_reduce_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, Cl, dWqkv, dgm, dbt, dWl, dbl);
+  HDF_LAUNCH_CHECK("hdf_dct_a_bwd/reduce");
+  return HDF_OK;
+}
+
+}  // extern "C"

@@ -202,11 +202,14 @@ class Engine:
         for l in range(4):
             q = f"{pre}layers.{l}."
             Cl = E + GROWTH * l
-            h0 = torch.empty((R, GROWTH), dtype=f32, device=dev)
-            ops.gemm(F[:, :Cl], P[q + "0.weight"], True, h0, bias=P[q + "0.bias"])
-            n1, m1, r1 = ops.layernorm_fwd(h0, P[q + "1.norm.weight"], P[q + "1.norm.bias"])
-            qkv = torch.empty((R, 3 * GROWTH), dtype=f32, device=dev)
-            ops.gemm(n1, P[q + "1.fn.to_qkv.weight"], True, qkv)
+            if self.fused_dct:
+                h0, n1, m1, r1, qkv = ops.dct_a_fwd(F, Cl, P, q)
+            else:
+                h0 = torch.empty((R, GROWTH), dtype=f32, device=dev)
+                ops.gemm(F[:, :Cl], P[q + "0.weight"], True, h0, bias=P[q + "0.bias"])
+                n1, m1, r1 = ops.layernorm_fwd(h0, P[q + "1.norm.weight"], P[q + "1.norm.bias"])
+                qkv = torch.empty((R, 3 * GROWTH), dtype=f32, device=dev)
+                ops.gemm(n1, P[q + "1.fn.to_qkv.weight"], True, qkv)
             o, lse = ops.attention_fwd(qkv, B, R // B, HEADS, (GROWTH // HEADS) ** -0.5)
             ida, idb, idc, idd, ide = ids(), ids(), ids(), ids(), ids()
             if self.fused_dct:
@@ -305,6 +308,9 @@ class Engine:
             else:
                 do, dh = self._dct_c_bwd_unfused(P, G, q, s, dF[:, Cl:Cl + GROWTH], R, p, seed)
             dqkv = ops.attention_bwd(s["qkv"], s["o"], do, s["lse"], B, R // B, HEADS, scale)
+            if self.fused_dct:
+                ops.dct_a_bwd(dqkv, dh, s, F, Cl, dF, P, G, q)
+                continue
             ops.gemm_at_b(dqkv, s["n1"], G[q + "1.fn.to_qkv.weight"])
             dn1 = torch.empty((R, GROWTH), dtype=f32, device=dev)
             ops.gemm(dqkv, P[q + "1.fn.to_qkv.weight"], False, dn1)

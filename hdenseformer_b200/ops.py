@@ -282,6 +282,32 @@ def add_rows_f32(dst, src, accumulate):
              "add_rows_f32")
 
 
+def dct_a_fwd(F, Cl, P, q):
+    """fused: h0 = F[:, :Cl] Wl^T + bl ; n1 = LN1(h0) ; qkv = n1 Wqkv^T.  Returns (h0, n1, m1, r1, qkv)."""
+    R = F.shape[0]
+    dev, f32 = F.device, torch.float32
+    h0 = torch.empty((R, 32), dtype=f32, device=dev)
+    n1 = torch.empty((R, 32), dtype=f32, device=dev)
+    m1 = torch.empty((R,), dtype=f32, device=dev)
+    r1 = torch.empty((R,), dtype=f32, device=dev)
+    qkv = torch.empty((R, 96), dtype=f32, device=dev)
+    _C.check(_lib().hdf_dct_a_fwd(_p(F), F.stride(0), Cl, _p(P[q + "0.weight"]), _p(P[q + "0.bias"]), _p(P[q + "1.norm.weight"]),
+                                  _p(P[q + "1.norm.bias"]), _p(P[q + "1.fn.to_qkv.weight"]), _p(h0), _p(n1), _p(m1), _p(r1),
+                                  _p(qkv), R, _s()), "dct_a_fwd")
+    return h0, n1, m1, r1, qkv
+
+
+def dct_a_bwd(dqkv, dh1, s, F, Cl, dF, P, G, q):
+    """fused backward of dct_a_fwd: dF[:, :Cl] += ..., parameter gradients += into G."""
+    R = F.shape[0]
+    ws = Workspace.get(_lib().hdf_dct_a_bwd_workspace(R, Cl))
+    _C.check(_lib().hdf_dct_a_bwd(_p(dqkv), _p(dh1), _p(s["h0"]), _p(s["n1"]), _p(s["m1"]), _p(s["r1"]), _p(F), F.stride(0), Cl,
+                                  _p(P[q + "1.fn.to_qkv.weight"]), _p(P[q + "1.norm.weight"]), _p(P[q + "0.weight"]), _p(dF),
+                                  dF.stride(0), _p(G[q + "1.fn.to_qkv.weight"]), _p(G[q + "1.norm.weight"]),
+                                  _p(G[q + "1.norm.bias"]), _p(G[q + "0.weight"]), _p(G[q + "0.bias"]), R, _p(ws), ws.numel(), _s()),
+             "dct_a_bwd")
+
+
 def dct_c_fwd(o, h0, P, q, fout, p, seed, ids):
     """fused: h1 = drop(o Wo^T + bo) + h0 ; h2 = FF(LN2(h1)) + h1 ; fout = FF(LN2(h2)).  Returns the saved tensors."""
     R = o.shape[0]

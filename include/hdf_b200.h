@@ -110,6 +110,13 @@ int hdf_dct_c_fwd(const float* o, const float* h0, float* h1, float* n2, float* 
                   const float* bo, const float* gm, const float* bt, const float* W1, const float* b1, const float* W2,
                   const float* b2, int R, float p, const unsigned long long* seed_ptr, unsigned long long seed, unsigned ida,
                   unsigned idb, unsigned idc, unsigned idd, unsigned ide, void* stream);
+int hdf_dct_a_fwd(const float* F, long long ldf, int Cl, const float* Wl, const float* bl, const float* gm, const float* bt,
+                  const float* Wqkv, float* h0, float* n1, float* m1, float* r1, float* qkv, int R, void* stream);
+size_t hdf_dct_a_bwd_workspace(int R, int Cl);
+int hdf_dct_a_bwd(const float* dqkv, const float* dh1, const float* h0, const float* n1, const float* m1, const float* r1,
+                  const float* F, long long ldf, int Cl, const float* Wqkv, const float* gm, const float* Wl, float* dF,
+                  long long lddf, float* dWqkv, float* dgm, float* dbt, float* dWl, float* dbl, int R, void* workspace,
+                  size_t ws_bytes, void* stream);   /* head of the layer: Linear_l + LN1 + to_qkv, and its backward */
 size_t hdf_dct_c_bwd_workspace(int R);
 int hdf_dct_c_bwd(const float* dg2, long long ldg, const float* o, const float* h1, const float* n2, const float* z1,
                   const float* f1, const float* h2, const float* n3, const float* z1b, const float* g1, const float* m2,

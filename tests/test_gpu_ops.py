@@ -309,3 +309,40 @@ def test_fused_dct_chain_matches_unfused_composition():
     assert rel(do_f, do_u) < 1e-4 and rel(dh_f, dh_u) < 1e-4
     for k in P:
         assert rel(Gf[k], Gu[k]) < 1e-4, k
+
+
+def test_fused_dct_head_matches_unfused_composition():
+    """hdf_dct_a_fwd / hdf_dct_a_bwd against gemm + layernorm + gemm composed from single-op kernels."""
+    torch.manual_seed(6)
+    R, FW = 2 * 27 + 3, 256
+    for Cl in (128, 224):
+        q = "l."
+        P = {q + "0.weight": torch.randn(32, Cl, device=DEV) * 0.1, q + "0.bias": torch.randn(32, device=DEV) * 0.1,
+             q + "1.norm.weight": 1 + 0.1 * torch.randn(32, device=DEV), q + "1.norm.bias": 0.1 * torch.randn(32, device=DEV),
+             q + "1.fn.to_qkv.weight": torch.randn(96, 32, device=DEV) * 0.2}
+        F = torch.randn(R, FW, device=DEV)
+        h0, n1, m1, r1, qkv = ops.dct_a_fwd(F, Cl, P, q)
+        h0u = torch.empty(R, 32, device=DEV)
+        ops.gemm(F[:, :Cl], P[q + "0.weight"], True, h0u, bias=P[q + "0.bias"])
+        n1u, m1u, r1u = ops.layernorm_fwd(h0u, P[q + "1.norm.weight"], P[q + "1.norm.bias"])
+        qkvu = torch.empty(R, 96, device=DEV)
+        ops.gemm(n1u, P[q + "1.fn.to_qkv.weight"], True, qkvu)
+        assert rel(h0, h0u) < 1e-5 and rel(n1, n1u) < 1e-5 and rel(qkv, qkvu) < 1e-5 and rel(r1, r1u) < 1e-5
+        dqkv, dh1 = torch.randn(R, 96, device=DEV), torch.randn(R, 32, device=DEV)
+        base = torch.randn(R, FW, device=DEV)
+        dF_f, dF_u = base.clone(), base.clone()
+        Gf = {k: torch.zeros_like(v) for k, v in P.items()}
+        Gu = {k: torch.zeros_like(v) for k, v in P.items()}
+        ops.dct_a_bwd(dqkv, dh1, dict(h0=h0, n1=n1, m1=m1, r1=r1), F, Cl, dF_f, P, Gf, q)
+        dh = dh1.clone()
+        ops.gemm_at_b(dqkv, n1u, Gu[q + "1.fn.to_qkv.weight"])
+        dn1 = torch.empty(R, 32, device=DEV)
+        ops.gemm(dqkv, P[q + "1.fn.to_qkv.weight"], False, dn1)
+        ops.layernorm_bwd(dn1, h0u, m1u, r1u, P[q + "1.norm.weight"], dh, True, Gu[q + "1.norm.weight"], Gu[q + "1.norm.bias"])
+        ops.gemm_at_b(dh, F[:, :Cl], Gu[q + "0.weight"])
+        ops.colsum(dh, Gu[q + "0.bias"], accumulate=True)
+        ops.gemm(dh, P[q + "0.weight"], False, dF_u[:, :Cl], accumulate=True)
+        assert rel(dF_f, dF_u) < 1e-4
+        assert torch.equal(dF_f[:, Cl:], base[:, Cl:])
+        for k in P:
+            assert rel(Gf[k], Gu[k]) < 1e-4, k
