@@ -88,6 +88,9 @@ class Engine:
         self.defer_wgrad = os.environ.get("HDF_NO_DEFER_WGRAD") is None
         self._deferred = []
         self.fused_dct = True     # fused post-attention chain kernels (csrc/dct.cu) instead of ~40 single-op launches
+        # fused layer-head kernels (Linear_l + LN1 + to_qkv): measured slower than the three single-op launches on B200
+        # (34.2 vs 33.1 ms/step), so they stay opt-in
+        self.fused_dct_head = os.environ.get("HDF_DCT_HEAD") == "1"
         self.use_side_stream = os.environ.get("HDF_NO_SIDE_STREAM") is None
         self._side = {}
         self._keep_alive = None
@@ -202,7 +205,7 @@ class Engine:
         for l in range(4):
             q = f"{pre}layers.{l}."
             Cl = E + GROWTH * l
-            if self.fused_dct:
+            if self.fused_dct_head:
                 h0, n1, m1, r1, qkv = ops.dct_a_fwd(F, Cl, P, q)
             else:
                 h0 = torch.empty((R, GROWTH), dtype=f32, device=dev)
@@ -308,7 +311,7 @@ class Engine:
             else:
                 do, dh = self._dct_c_bwd_unfused(P, G, q, s, dF[:, Cl:Cl + GROWTH], R, p, seed)
             dqkv = ops.attention_bwd(s["qkv"], s["o"], do, s["lse"], B, R // B, HEADS, scale)
-            if self.fused_dct:
+            if self.fused_dct_head:
                 ops.dct_a_bwd(dqkv, dh, s, F, Cl, dF, P, G, q)
                 continue
             ops.gemm_at_b(dqkv, s["n1"], G[q + "1.fn.to_qkv.weight"])
