@@ -45,9 +45,25 @@ __global__ void __launch_bounds__(256) rowreduce_kernel(F f, int V, int C, int r
 #pragma unroll
   for (int i = 0; i < VEC; ++i) sa[i] = sb[i] = 0.f;
   if (r < rpi) {
-    for (int v = v0 + r; v < v1; v += rpi) {
+    // the thread's channel group is fixed: per-channel constants live in registers, and four independent rows are
+    // in flight per iteration (a single 16-byte load per thread cannot cover the HBM latency on B200)
+    typename F::template Coef<VEC> k;
+    f.template prep<VEC>(n, cg * VEC, k);
+    int v = v0 + r;
+    // (fp32 tensors keep the plain sequential order: that path is the bit-exact-argmax reference path, not the fast one)
+    for (; sizeof(T) == 2 && v + 3 * rpi < v1; v += 4 * rpi) {
+      float a[4][VEC], b[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) f.template eval<VEC>(n, v + u * rpi, cg * VEC, k, a[u], b[u]);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        sa[i] += (a[0][i] + a[1][i]) + (a[2][i] + a[3][i]);
+        sb[i] += (b[0][i] + b[1][i]) + (b[2][i] + b[3][i]);
+      }
+    }
+    for (; v < v1; v += rpi) {
       float a[VEC], b[VEC];
-      f.template eval<VEC>(n, v, cg * VEC, a, b);
+      f.template eval<VEC>(n, v, cg * VEC, k, a, b);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) { sa[i] += a[i]; sb[i] += b[i]; }
     }
@@ -66,28 +82,44 @@ __global__ void __launch_bounds__(256) rowreduce_kernel(F f, int V, int C, int r
   }
 }
 
+struct NoCoef {};
+
 template <typename T>
 struct StatsF {
   const T* y; long long ld; long long V;
-  template <int VEC> __device__ void eval(int n, int v, int c, float* a, float* b) const {
+  template <int VEC> using Coef = NoCoef;
+  template <int VEC> __device__ void prep(int, int, NoCoef&) const {}
+  template <int VEC> __device__ void eval(int n, int v, int c, const NoCoef&, float* a, float* b) const {
     loadv<T, VEC>(y + ((long long)n * V + v) * ld + c, a);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) b[i] = a[i] * a[i];
   }
 };
 
+template <int VEC> struct InBwdCoef { float m[VEC], rs[VEC], gm[VEC], bt[VEC]; };
+
 template <typename T>
 struct InBwdF {
   const T* dout; long long ldd; const T* y; long long ldy; long long V;
   const float* mean; const float* rstd; const float* gamma; const float* beta; int C; int relu;
-  template <int VEC> __device__ void eval(int n, int v, int c, float* a, float* b) const {
+  template <int VEC> using Coef = InBwdCoef<VEC>;
+  template <int VEC> __device__ void prep(int n, int c, InBwdCoef<VEC>& k) const {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      k.m[i] = mean[n * C + c + i];
+      k.rs[i] = rstd[n * C + c + i];
+      k.gm[i] = gamma ? gamma[c + i] : 1.f;
+      k.bt[i] = beta ? beta[c + i] : 0.f;
+    }
+  }
+  template <int VEC> __device__ void eval(int n, int v, int c, const InBwdCoef<VEC>& k, float* a, float* b) const {
     float g[VEC], x[VEC];
     loadv<T, VEC>(dout + ((long long)n * V + v) * ldd + c, g);
     loadv<T, VEC>(y + ((long long)n * V + v) * ldy + c, x);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float xh = (x[i] - mean[n * C + c + i]) * rstd[n * C + c + i];
-      const float z = xh * (gamma ? gamma[c + i] : 1.f) + (beta ? beta[c + i] : 0.f);
+      const float xh = (x[i] - k.m[i]) * k.rs[i];
+      const float z = xh * k.gm[i] + k.bt[i];
       const float dz = (!relu || z > 0.f) ? g[i] : 0.f;
       a[i] = dz;
       b[i] = dz * xh;
@@ -98,7 +130,9 @@ struct InBwdF {
 template <typename T>
 struct ColSumF {
   const T* x; long long ld; long long V;
-  template <int VEC> __device__ void eval(int n, int v, int c, float* a, float* b) const {
+  template <int VEC> using Coef = NoCoef;
+  template <int VEC> __device__ void prep(int, int, NoCoef&) const {}
+  template <int VEC> __device__ void eval(int n, int v, int c, const NoCoef&, float* a, float* b) const {
     loadv<T, VEC>(x + ((long long)n * V + v) * ld + c, a);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) b[i] = 0.f;
@@ -252,6 +286,143 @@ __global__ void in_bwd_apply_kernel(const T* __restrict__ dout, long long ldd, c
   }
 }
 
+// Fast forms for the common case 256 % (C/VEC) == 0: grid (row chunks, N); a thread keeps one channel group for its whole
+// life, so the per-channel statistics / affine constants sit in registers (the generic kernels above re-read 4-6
+// scalars per element and pay two 64-bit divisions per vector), and four rows are in flight per iteration.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) in_apply_fast_kernel(const T* __restrict__ y, long long ldy, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const T* __restrict__ res,
+                                                           long long ldr, T* __restrict__ out, long long ldo, int V, int C,
+                                                           int relu, int rows_per_block) {
+  const int cpv = C / VEC, rpi = 256 / cpv;
+  const int cg = threadIdx.x % cpv, r = threadIdx.x / cpv, n = blockIdx.y, c = cg * VEC;
+  float m[VEC], a[VEC], b[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    m[k] = mean[n * C + c + k];
+    a[k] = rstd[n * C + c + k];
+    b[k] = beta ? beta[c + k] : 0.f;
+  }
+  float gm[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) gm[k] = gamma ? gamma[c + k] : 1.f;
+  const int v0 = blockIdx.x * rows_per_block, v1 = min(V, v0 + rows_per_block);
+  const T* yp = y + (long long)n * V * ldy + c;
+  const T* rp = res ? res + (long long)n * V * ldr + c : nullptr;
+  T* op = out + (long long)n * V * ldo + c;
+  const bool has_res = rp != nullptr;
+  auto one = [&](float* x, const float* rr) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float z = (x[k] - m[k]) * a[k];
+      z = z * gm[k] + b[k];
+      if (relu) z = fmaxf(z, 0.f);
+      if (has_res) z += rr[k];
+      x[k] = z;
+    }
+  };
+  int v = v0 + r;
+  for (; v + 3 * rpi < v1; v += 4 * rpi) {
+    float x[4][VEC], rr[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) loadv<T, VEC>(yp + (long long)(v + u * rpi) * ldy, x[u]);
+    if (has_res) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) loadv<T, VEC>(rp + (long long)(v + u * rpi) * ldr, rr[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) rr[u][k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      one(x[u], rr[u]);
+      storev<T, VEC>(op + (long long)(v + u * rpi) * ldo, x[u]);
+    }
+  }
+  for (; v < v1; v += rpi) {
+    float x[VEC], rr[VEC];
+    loadv<T, VEC>(yp + (long long)v * ldy, x);
+    if (has_res) loadv<T, VEC>(rp + (long long)v * ldr, rr);
+    else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) rr[k] = 0.f;
+    }
+    one(x, rr);
+    storev<T, VEC>(op + (long long)v * ldo, x);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) in_bwd_apply_fast_kernel(const T* __restrict__ dout, long long ldd, const T* __restrict__ y,
+                                                               long long ldy, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ s1,
+                                                               const float* __restrict__ s2, T* __restrict__ dy, long long ldo,
+                                                               int V, int C, int relu, int rows_per_block) {
+  const int cpv = C / VEC, rpi = 256 / cpv;
+  const int cg = threadIdx.x % cpv, r = threadIdx.x / cpv, n = blockIdx.y, c = cg * VEC;
+  const float invV = 1.f / (float)V;
+  float m[VEC], rs[VEC], gm[VEC], bt[VEC], q1[VEC], q2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const int nc = n * C + c + k;
+    m[k] = mean[nc];
+    rs[k] = rstd[nc];
+    gm[k] = gamma ? gamma[c + k] : 1.f;
+    bt[k] = beta ? beta[c + k] : 0.f;
+    q1[k] = s1[nc] * invV;
+    q2[k] = s2[nc] * invV;
+  }
+  const int v0 = blockIdx.x * rows_per_block, v1 = min(V, v0 + rows_per_block);
+  const T* gp = dout + (long long)n * V * ldd + c;
+  const T* yp = y + (long long)n * V * ldy + c;
+  T* op = dy + (long long)n * V * ldo + c;
+  auto one = [&](const float* g, float* x) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float xh = (x[k] - m[k]) * rs[k];
+      const float z = xh * gm[k] + bt[k];
+      const float dz = (!relu || z > 0.f) ? g[k] : 0.f;
+      x[k] = gm[k] * rs[k] * (dz - q1[k] - xh * q2[k]);
+    }
+  };
+  int v = v0 + r;
+  for (; v + 3 * rpi < v1; v += 4 * rpi) {
+    float g[4][VEC], x[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      loadv<T, VEC>(gp + (long long)(v + u * rpi) * ldd, g[u]);
+      loadv<T, VEC>(yp + (long long)(v + u * rpi) * ldy, x[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      one(g[u], x[u]);
+      storev<T, VEC>(op + (long long)(v + u * rpi) * ldo, x[u]);
+    }
+  }
+  for (; v < v1; v += rpi) {
+    float g[VEC], x[VEC];
+    loadv<T, VEC>(gp + (long long)v * ldd, g);
+    loadv<T, VEC>(yp + (long long)v * ldy, x);
+    one(g, x);
+    storev<T, VEC>(op + (long long)v * ldo, x);
+  }
+}
+
+// rows per block for the fast elementwise kernels: ~8 resident-CTA waves over the 148 SMs, >= 4 passes of the block
+inline int fast_rows_per_block(long long V, int N, int rpi) {
+  long long target = (148ll * 16 + N - 1) / N;
+  long long rpb = (V + target - 1) / target;
+  const long long unit = 4ll * rpi;
+  rpb = (rpb + unit - 1) / unit * unit;
+  return (int)(rpb < unit ? unit : rpb);
+}
+inline bool fast_ok(int C, int vec, long long V) { const int cpv = C / vec; return cpv >= 1 && cpv <= 256 && 256 % cpv == 0 && V < (1ll << 31); }
+
 template <typename T, int VEC>
 __global__ void add_kernel(T* __restrict__ dst, long long ldd, const T* __restrict__ src, long long lds, int C,
                            long long total) {
@@ -301,63 +472,71 @@ __global__ void uncast_rows_kernel(const T* __restrict__ src, long long lds, flo
   }
 }
 
+// The spatial kernels below run one block per (n, d, h) line: the line coordinates come from blockIdx (a few 32-bit
+// divisions per block), a thread walks the (w, channel-group) items of the line.
+
 // 2x2x2 max pool, first maximum in (kd,kh,kw) scan order wins (torch semantics: strict '>' update)
 template <typename T, int VEC>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo, int Do,
-                                   int Ho, int Wo, int C, long long total) {
+                                   int Ho, int Wo, int C) {
   const int cpv = C / VEC;
   const int Hi = 2 * Ho, Wi = 2 * Wo, Di = 2 * Do;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cpv) * VEC;
-    long long r = i / cpv;
-    const int w = r % Wo; r /= Wo;
-    const int h = r % Ho; r /= Ho;
-    const int d = r % Do;
-    const long long n = r / Do;
+  int line = blockIdx.x;
+  const int h = line % Ho; line /= Ho;
+  const int d = line % Do;
+  const long long n = line / Do;
+  const T* xin = x + (((n * Di + 2 * d) * Hi + 2 * h) * (long long)Wi) * ldx;
+  T* orow = out + ((long long)blockIdx.x * Wo) * ldo;
+  for (int i = threadIdx.x; i < Wo * cpv; i += blockDim.x) {
+    const int w = i / cpv, c = (i - w * cpv) * VEC;
     float m[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+    float v[8][VEC];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      loadv<T, VEC>(xin + (((long long)(t >> 2) * Hi + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1)) * ldx + c, v[t]);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      const long long row = ((n * Di + 2 * d + (t >> 2)) * Hi + 2 * h + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1);
-      float v[VEC];
-      loadv<T, VEC>(x + row * ldx + c, v);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) m[k] = (v[k] > m[k] || v[k] != v[k]) ? v[k] : m[k];
+      for (int k = 0; k < VEC; ++k) m[k] = (v[t][k] > m[k] || v[t][k] != v[t][k]) ? v[t][k] : m[k];
     }
-    storev<T, VEC>(out + (i / cpv) * ldo + c, m);
+    storev<T, VEC>(orow + (long long)w * ldo + c, m);
   }
 }
 
 // dx[argmax] (+)= dpool ; other 7 positions get 0 when !accumulate
 template <typename T, int VEC>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ dp, long long ldp,
-                                   T* __restrict__ dx, long long lddx, int Do, int Ho, int Wo, int C, int accumulate,
-                                   long long total) {
+                                   T* __restrict__ dx, long long lddx, int Do, int Ho, int Wo, int C, int accumulate) {
   const int cpv = C / VEC;
   const int Hi = 2 * Ho, Wi = 2 * Wo, Di = 2 * Do;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cpv) * VEC;
-    long long r = i / cpv;
-    const int w = r % Wo; r /= Wo;
-    const int h = r % Ho; r /= Ho;
-    const int d = r % Do;
-    const long long n = r / Do;
+  int line = blockIdx.x;
+  const int h = line % Ho; line /= Ho;
+  const int d = line % Do;
+  const long long n = line / Do;
+  const long long row0 = ((n * Di + 2 * d) * Hi + 2 * h) * (long long)Wi;
+  const T* prow = dp + ((long long)blockIdx.x * Wo) * ldp;
+  for (int i = threadIdx.x; i < Wo * cpv; i += blockDim.x) {
+    const int w = i / cpv, c = (i - w * cpv) * VEC;
     float m[VEC], g[VEC];
     int am[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) { m[k] = -INFINITY; am[k] = 0; }
     long long rows[8];
+    float v[8][VEC];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      rows[t] = ((n * Di + 2 * d + (t >> 2)) * Hi + 2 * h + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1);
-      float v[VEC];
-      loadv<T, VEC>(x + rows[t] * ldx + c, v);
+      rows[t] = row0 + ((long long)(t >> 2) * Hi + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1);
+      loadv<T, VEC>(x + rows[t] * ldx + c, v[t]);
+    }
+    loadv<T, VEC>(prow + (long long)w * ldp + c, g);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
 #pragma unroll
       for (int k = 0; k < VEC; ++k)
-        if (v[k] > m[k] || v[k] != v[k]) { m[k] = v[k]; am[k] = t; }
+        if (v[t][k] > m[k] || v[t][k] != v[t][k]) { m[k] = v[t][k]; am[k] = t; }
     }
-    loadv<T, VEC>(dp + (i / cpv) * ldp + c, g);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       float o[VEC];
@@ -380,34 +559,48 @@ __device__ __forceinline__ void up2_src(int o, int In, int& i0, int& i1, float& 
 
 template <typename T, int VEC>
 __global__ void upsample2_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo, int Di,
-                                     int Hi, int Wi, int C, long long total) {
+                                     int Hi, int Wi, int C) {
   const int cpv = C / VEC;
   const int Do = 2 * Di, Ho = 2 * Hi, Wo = 2 * Wi;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cpv) * VEC;
-    long long r = i / cpv;
-    const int w = r % Wo; r /= Wo;
-    const int h = r % Ho; r /= Ho;
-    const int d = r % Do;
-    const long long n = r / Do;
-    int d0, d1, h0, h1, w0, w1;
-    float fd, fh, fw;
-    up2_src(d, Di, d0, d1, fd);
-    up2_src(h, Hi, h0, h1, fh);
+  int line = blockIdx.x;
+  const int h = line % Ho; line /= Ho;
+  const int d = line % Do;
+  const long long n = line / Do;
+  int d0, d1, h0, h1;
+  float fd, fh;
+  up2_src(d, Di, d0, d1, fd);
+  up2_src(h, Hi, h0, h1, fh);
+  const T* l00 = x + (((n * Di + d0) * Hi + h0) * (long long)Wi) * ldx;
+  const T* l01 = x + (((n * Di + d0) * Hi + h1) * (long long)Wi) * ldx;
+  const T* l10 = x + (((n * Di + d1) * Hi + h0) * (long long)Wi) * ldx;
+  const T* l11 = x + (((n * Di + d1) * Hi + h1) * (long long)Wi) * ldx;
+  const float w00 = (1.f - fd) * (1.f - fh), w01 = (1.f - fd) * fh, w10 = fd * (1.f - fh), w11 = fd * fh;
+  T* orow = out + ((long long)blockIdx.x * Wo) * ldo;
+  for (int i = threadIdx.x; i < Wo * cpv; i += blockDim.x) {
+    const int w = i / cpv, c = (i - w * cpv) * VEC;
+    int w0, w1;
+    float fw;
     up2_src(w, Wi, w0, w1, fw);
+    float v[8][VEC];
+    loadv<T, VEC>(l00 + (long long)w0 * ldx + c, v[0]);
+    loadv<T, VEC>(l00 + (long long)w1 * ldx + c, v[1]);
+    loadv<T, VEC>(l01 + (long long)w0 * ldx + c, v[2]);
+    loadv<T, VEC>(l01 + (long long)w1 * ldx + c, v[3]);
+    loadv<T, VEC>(l10 + (long long)w0 * ldx + c, v[4]);
+    loadv<T, VEC>(l10 + (long long)w1 * ldx + c, v[5]);
+    loadv<T, VEC>(l11 + (long long)w0 * ldx + c, v[6]);
+    loadv<T, VEC>(l11 + (long long)w1 * ldx + c, v[7]);
     float acc[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    // same accumulation order as the (d,h,w)-bit enumeration t = 0..7 of the weights
+    const float wt[8] = {w00 * (1.f - fw), w00 * fw, w01 * (1.f - fw), w01 * fw, w10 * (1.f - fw), w10 * fw, w11 * (1.f - fw), w11 * fw};
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      const int dd = (t & 4) ? d1 : d0, hh = (t & 2) ? h1 : h0, ww = (t & 1) ? w1 : w0;
-      const float wt = ((t & 4) ? fd : 1.f - fd) * ((t & 2) ? fh : 1.f - fh) * ((t & 1) ? fw : 1.f - fw);
-      float v[VEC];
-      loadv<T, VEC>(x + (((n * Di + dd) * Hi + hh) * Wi + ww) * ldx + c, v);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt[t], v[t][k], acc[k]);
     }
-    storev<T, VEC>(out + (i / cpv) * ldo + c, acc);
+    storev<T, VEC>(orow + (long long)w * ldo + c, acc);
   }
 }
 
@@ -422,43 +615,52 @@ __device__ __forceinline__ void up2_bwd_taps(int i, int In, int* o, float* w) {
 
 template <typename T, int VEC>
 __global__ void upsample2_bwd_kernel(const T* __restrict__ dout, long long ldd, T* __restrict__ dx, long long lddx, int Di,
-                                     int Hi, int Wi, int C, int accumulate, long long total) {
+                                     int Hi, int Wi, int C, int accumulate) {
   const int cpv = C / VEC;
   const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cpv) * VEC;
-    long long r = i / cpv;
-    const int w = r % Wi; r /= Wi;
-    const int h = r % Hi; r /= Hi;
-    const int d = r % Di;
-    const long long n = r / Di;
-    int od[4], oh[4], ow[4];
-    float wd[4], wh[4], ww[4];
-    up2_bwd_taps(d, Di, od, wd);
-    up2_bwd_taps(h, Hi, oh, wh);
+  int line = blockIdx.x;
+  const int h = line % Hi; line /= Hi;
+  const int d = line % Di;
+  const long long n = line / Di;
+  int od[4], oh[4];
+  float wd[4], wh[4];
+  up2_bwd_taps(d, Di, od, wd);
+  up2_bwd_taps(h, Hi, oh, wh);
+  T* xrow = dx + ((long long)blockIdx.x * Wi) * lddx;
+  for (int i = threadIdx.x; i < Wi * cpv; i += blockDim.x) {
+    const int w = i / cpv, c = (i - w * cpv) * VEC;
+    int ow[4];
+    float ww[4];
     up2_bwd_taps(w, Wi, ow, ww);
     float acc[VEC];
-    if (accumulate) loadv<T, VEC>(dx + (i / cpv) * lddx + c, acc);
+    if (accumulate) loadv<T, VEC>(xrow + (long long)w * lddx + c, acc);
     else {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
     }
+#pragma unroll
     for (int a = 0; a < 4; ++a) {
       if (wd[a] == 0.f) continue;
+#pragma unroll
       for (int b = 0; b < 4; ++b) {
         if (wh[b] == 0.f) continue;
+        const T* lrow = dout + (((n * Do + od[a]) * Ho + oh[b]) * (long long)Wo) * ldd + c;
+        const float wab = wd[a] * wh[b];
+        float v[4][VEC];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (ww[e] != 0.f) loadv<T, VEC>(lrow + (long long)ow[e] * ldd, v[e]);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (ww[e] == 0.f) continue;
-          const float wt = wd[a] * wh[b] * ww[e];
-          float v[VEC];
-          loadv<T, VEC>(dout + (((n * Do + od[a]) * Ho + oh[b]) * Wo + ow[e]) * ldd + c, v);
+          const float wt = wab * ww[e];
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+          for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt, v[e][k], acc[k]);
         }
       }
     }
-    storev<T, VEC>(dx + (i / cpv) * lddx + c, acc);
+    storev<T, VEC>(xrow + (long long)w * lddx + c, acc);
   }
 }
 
@@ -528,35 +730,58 @@ __global__ void head_dgrad_kernel(const T* __restrict__ g, const float* __restri
   }
 }
 
-// partial[chunk][k][C+1]: dW[k][c] = sum_v g[k][v] a[v][c];  column C holds db[k].
-// Thread = (row lane, VEC-channel group): 128-bit loads of the activation row, coalesced loads of g.
-template <typename T, int VEC>
+// partial[n][chunk][k][C+1]: dW[k][c] = sum_v g[k][v] a[v][c];  column C holds db[k].
+// grid (chunks, N).  Thread = (row lane, VEC-channel group): 128-bit loads of the activation row, U rows in flight.
+// NC = class-count bucket (2, 4 or 8) so that two-class heads do not carry 64 dead accumulators (1 CTA/SM before).
+template <typename T, int VEC, int NC>
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ a, long long lda,
-                                                        long long V, int C, int ncls, long long total, int rows_per_chunk,
+                                                        int V, int C, int ncls, int rows_per_chunk,
                                                         float* __restrict__ partial) {
   extern __shared__ float sm[];  // [lanes][ncls][C] then [lanes][ncls]
+  constexpr int U = NC <= 2 ? 8 : 4;
   const int tid = threadIdx.x;
   const int cpv = C / VEC;                 // channel groups per row (<= 256 guaranteed by host)
   const int lanes = 256 / cpv;
   const int lane = tid / cpv, cg = tid % cpv;
-  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
-  const long long r1 = min(total, r0 + rows_per_chunk);
-  float acc[MAXCLS][VEC], accb[MAXCLS];
+  const int n = blockIdx.y;
+  const int v0 = blockIdx.x * rows_per_chunk, v1 = min(V, v0 + rows_per_chunk);
+  const T* gp = g + (long long)n * ncls * V;
+  const T* ap = a + (long long)n * V * lda + cg * VEC;
+  float acc[NC][VEC], accb[NC];
 #pragma unroll
-  for (int k = 0; k < MAXCLS; ++k) {
+  for (int k = 0; k < NC; ++k) {
     accb[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[k][j] = 0.f;
   }
   if (lane < lanes) {
-    for (long long row = r0 + lane; row < r1; row += lanes) {
-      const long long n = row / V, v = row % V;
-      float x[VEC];
-      loadv<T, VEC>(a + row * lda + cg * VEC, x);
+    int v = v0 + lane;
+    for (; v + (U - 1) * lanes < v1; v += U * lanes) {
+      float x[U][VEC], gv[U][NC];
 #pragma unroll
-      for (int k = 0; k < MAXCLS; ++k) {
+      for (int u = 0; u < U; ++u) loadv<T, VEC>(ap + (long long)(v + u * lanes) * lda, x[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) gv[u][k] = (k < ncls) ? to_f(gp[(long long)k * V + v + u * lanes]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          accb[k] += gv[u][k];
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(gv[u][k], x[u][j], acc[k][j]);
+        }
+      }
+    }
+    for (; v < v1; v += lanes) {
+      float x[VEC];
+      loadv<T, VEC>(ap + (long long)v * lda, x);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
         if (k < ncls) {
-          const float gv = to_f(g[(n * ncls + k) * V + v]);
+          const float gv = to_f(gp[(long long)k * V + v]);
           accb[k] += gv;
 #pragma unroll
           for (int j = 0; j < VEC; ++j) acc[k][j] = fmaf(gv, x[j], acc[k][j]);
@@ -564,7 +789,7 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const T* __restrict__ g
       }
     }
 #pragma unroll
-    for (int k = 0; k < MAXCLS; ++k) {
+    for (int k = 0; k < NC; ++k) {
       if (k < ncls) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) sm[(lane * ncls + k) * C + cg * VEC + j] = acc[k][j];
@@ -573,17 +798,67 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const T* __restrict__ g
     }
   }
   __syncthreads();
+  const long long blk = (long long)n * gridDim.x + blockIdx.x;
   for (int i = tid; i < ncls * C; i += 256) {
     float s2 = 0.f;
     for (int l = 0; l < lanes; ++l) s2 += sm[l * ncls * C + i];
     const int k = i / C, c = i % C;
-    partial[((long long)blockIdx.x * ncls + k) * (C + 1) + c] = s2;
+    partial[(blk * ncls + k) * (C + 1) + c] = s2;
   }
   if (tid < ncls) {
     float s2 = 0.f;
     for (int l = 0; l < lanes; ++l) s2 += sm[lanes * ncls * C + l * ncls + tid];
-    partial[((long long)blockIdx.x * ncls + tid) * (C + 1) + C] = s2;
+    partial[(blk * ncls + tid) * (C + 1) + C] = s2;
   }
+}
+
+template <typename T, int VEC, int NC>
+void launch_head_wgrad(dim3 grid, size_t smem, cudaStream_t s, const T* g, const T* a, long long lda, int V, int C, int ncls,
+                       int rpc, float* partial) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(head_wgrad_kernel<T, VEC, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  head_wgrad_kernel<T, VEC, NC><<<grid, 256, smem, s>>>(g, a, lda, V, C, ncls, rpc, partial);
+}
+
+// da[n, v, c] (+)= sum_k g[n, k, v] * w[k, c]; same thread layout as the weight gradient: a warp writes whole rows
+// (the row-per-thread kernel above stores 16 bytes per lane at a 2*C-byte stride: half-filled sectors)
+template <typename T, int VEC, int NC>
+__global__ void __launch_bounds__(256) head_dgrad_fast_kernel(const T* __restrict__ g, const float* __restrict__ w,
+                                                             T* __restrict__ da, long long ldd, int V, int C, int ncls,
+                                                             int accumulate, int rows_per_block) {
+  const int cpv = C / VEC, lanes = 256 / cpv;
+  const int lane = threadIdx.x / cpv, cg = threadIdx.x % cpv, n = blockIdx.y;
+  float wk[NC][VEC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) wk[k][j] = (k < ncls) ? w[k * C + cg * VEC + j] : 0.f;
+  }
+  const int v0 = blockIdx.x * rows_per_block, v1 = min(V, v0 + rows_per_block);
+  const T* gp = g + (long long)n * ncls * V;
+  T* dp = da + (long long)n * V * ldd + cg * VEC;
+  auto one = [&](int v) {
+    float o[VEC];
+    if (accumulate) loadv<T, VEC>(dp + (long long)v * ldd, o);
+    else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      if (k < ncls) {
+        const float gv = to_f(gp[(long long)k * V + v]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = fmaf(gv, wk[k][j], o[j]);
+      }
+    }
+    storev<T, VEC>(dp + (long long)v * ldd, o);
+  };
+  int v = v0 + lane;
+  for (; v + 3 * lanes < v1; v += 4 * lanes) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(v + u * lanes);
+  }
+  for (; v < v1; v += lanes) one(v);
 }
 
 __global__ void head_wgrad_finalize_kernel(const float* __restrict__ partial, int chunks, int C, int ncls,
@@ -605,6 +880,13 @@ __global__ void ncdhw_to_cl_kernel(const float* __restrict__ x, T* __restrict__ 
     const long long n = i / V, v = i % V;
     for (int c = 0; c < C; ++c) out[i * ldo + c] = from_f<T>(x[(n * C + c) * V + v]);
   }
+}
+
+// threads per line-block: the smallest multiple of 32 (<= 256) that covers the line's items in the fewest passes
+int line_block(int items) {
+  const int passes = (items + 255) / 256;
+  int t = ((items + passes - 1) / passes + 31) / 32 * 32;
+  return t < 32 ? 32 : (t > 256 ? 256 : t);
 }
 
 int grid_for(long long total, int block = 256) {
@@ -646,8 +928,14 @@ int hdf_instnorm_apply(int dtype, const void* y, long long ldy, const float* mea
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(y, ldy, C) && can_vec<T>(out, ldo, C) && (!residual || can_vec<T>(residual, ldr, C));
-    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * V * (C / VEC);
-        in_apply_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)y, ldy, mean, rstd, gamma, beta, (const T*)residual, ldr, (T*)out, ldo, V, C, relu, total); });
+    HDF_VEC_DISPATCH(vec, {
+        if (vec && sizeof(T) == 2 && fast_ok(C, VEC, V)) {
+          const int rpb = fast_rows_per_block(V, N, 256 / (C / VEC));
+          in_apply_fast_kernel<T, VEC><<<dim3((unsigned)cdiv(V, rpb), N), 256, 0, s>>>((const T*)y, ldy, mean, rstd, gamma, beta, (const T*)residual, ldr, (T*)out, ldo, (int)V, C, relu, rpb);
+        } else {
+          long long total = (long long)N * V * (C / VEC);
+          in_apply_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)y, ldy, mean, rstd, gamma, beta, (const T*)residual, ldr, (T*)out, ldo, V, C, relu, total);
+        } });
   });
   HDF_LAUNCH_CHECK("hdf_instnorm_apply");
   return HDF_OK;
@@ -675,8 +963,14 @@ int hdf_instnorm_bwd(int dtype, const void* dout, long long ldd, const void* y, 
   }
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(dout, ldd, C) && can_vec<T>(y, ldy, C) && can_vec<T>(dy, ldo, C);
-    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * V * (C / VEC);
-        in_bwd_apply_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)dout, ldd, (const T*)y, ldy, mean, rstd, gamma, beta, s1, s2, (T*)dy, ldo, V, C, relu, total); });
+    HDF_VEC_DISPATCH(vec, {
+        if (vec && sizeof(T) == 2 && fast_ok(C, VEC, V)) {
+          const int rpb = fast_rows_per_block(V, N, 256 / (C / VEC));
+          in_bwd_apply_fast_kernel<T, VEC><<<dim3((unsigned)cdiv(V, rpb), N), 256, 0, s>>>((const T*)dout, ldd, (const T*)y, ldy, mean, rstd, gamma, beta, s1, s2, (T*)dy, ldo, (int)V, C, relu, rpb);
+        } else {
+          long long total = (long long)N * V * (C / VEC);
+          in_bwd_apply_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)dout, ldd, (const T*)y, ldy, mean, rstd, gamma, beta, s1, s2, (T*)dy, ldo, V, C, relu, total);
+        } });
   });
   HDF_LAUNCH_CHECK("hdf_instnorm_bwd/apply");
   return HDF_OK;
@@ -748,7 +1042,7 @@ int hdf_maxpool2_fwd(int dtype, const void* x, long long ldx, void* out, long lo
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(out, ldo, C);
-    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * Do * Ho * Wo * (C / VEC); maxpool_fwd_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)x, ldx, (T*)out, ldo, Do, Ho, Wo, C, total); });
+    HDF_VEC_DISPATCH(vec, { maxpool_fwd_kernel<T, VEC><<<(unsigned)((long long)N * Do * Ho), line_block(Wo * (C / VEC)), 0, s>>>((const T*)x, ldx, (T*)out, ldo, Do, Ho, Wo, C); });
   });
   HDF_LAUNCH_CHECK("hdf_maxpool2_fwd");
   return HDF_OK;
@@ -760,7 +1054,7 @@ int hdf_maxpool2_bwd(int dtype, const void* x, long long ldx, const void* dpool,
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(dpool, ldp, C) && can_vec<T>(dx, lddx, C);
-    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * Do * Ho * Wo * (C / VEC); maxpool_bwd_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)x, ldx, (const T*)dpool, ldp, (T*)dx, lddx, Do, Ho, Wo, C, accumulate, total); });
+    HDF_VEC_DISPATCH(vec, { maxpool_bwd_kernel<T, VEC><<<(unsigned)((long long)N * Do * Ho), line_block(Wo * (C / VEC)), 0, s>>>((const T*)x, ldx, (const T*)dpool, ldp, (T*)dx, lddx, Do, Ho, Wo, C, accumulate); });
   });
   HDF_LAUNCH_CHECK("hdf_maxpool2_bwd");
   return HDF_OK;
@@ -772,7 +1066,7 @@ int hdf_upsample2_fwd(int dtype, const void* x, long long ldx, void* out, long l
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(out, ldo, C);
-    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * Di * Hi * Wi * 8 * (C / VEC); upsample2_fwd_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)x, ldx, (T*)out, ldo, Di, Hi, Wi, C, total); });
+    HDF_VEC_DISPATCH(vec, { upsample2_fwd_kernel<T, VEC><<<(unsigned)((long long)N * Di * Hi * 4), line_block(2 * Wi * (C / VEC)), 0, s>>>((const T*)x, ldx, (T*)out, ldo, Di, Hi, Wi, C); });
   });
   HDF_LAUNCH_CHECK("hdf_upsample2_fwd");
   return HDF_OK;
@@ -784,7 +1078,7 @@ int hdf_upsample2_bwd(int dtype, const void* dout, long long ldd, void* dx, long
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(dout, ldd, C) && can_vec<T>(dx, lddx, C);
-    HDF_VEC_DISPATCH(vec, { long long total = (long long)N * Di * Hi * Wi * (C / VEC); upsample2_bwd_kernel<T, VEC><<<grid_for(total), 256, 0, s>>>((const T*)dout, ldd, (T*)dx, lddx, Di, Hi, Wi, C, accumulate, total); });
+    HDF_VEC_DISPATCH(vec, { upsample2_bwd_kernel<T, VEC><<<(unsigned)((long long)N * Di * Hi), line_block(Wi * (C / VEC)), 0, s>>>((const T*)dout, ldd, (T*)dx, lddx, Di, Hi, Wi, C, accumulate); });
   });
   HDF_LAUNCH_CHECK("hdf_upsample2_bwd");
   return HDF_OK;
@@ -804,11 +1098,14 @@ int hdf_head_fwd(int dtype, const void* a, long long lda, const float* w, const 
   return HDF_OK;
 }
 
+static int head_chunks_per_n(int N, long long V) {
+  long long c = (V + 2047) / 2048, cap = (148 * 4 + N - 1) / N;
+  if (c > cap) c = cap;
+  return (int)(c < 1 ? 1 : c);
+}
+
 size_t hdf_head_bwd_workspace(int N, long long V, int C, int ncls) {
-  const long long total = (long long)N * V;
-  int chunks = (int)((total + 2047) / 2048);
-  if (chunks > 148 * 4) chunks = 148 * 4;
-  return (size_t)chunks * ncls * (C + 1) * sizeof(float);
+  return (size_t)N * head_chunks_per_n(N, V) * ncls * (C + 1) * sizeof(float);
 }
 
 // g: NCDHW [N, ncls, V] (T).  da (+)= g . w ; dw/db (+)= reductions
@@ -818,11 +1115,12 @@ int hdf_head_bwd(int dtype, const void* g, const void* a, long long lda, const f
   HDF_REQUIRE(g && a && w && da && dw && workspace && ncls >= 1 && ncls <= MAXCLS, "hdf_head_bwd: bad args");
   HDF_REQUIRE(ws_bytes >= hdf_head_bwd_workspace(N, V, C, ncls), "hdf_head_bwd: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
+  HDF_REQUIRE(V < (1ll << 31), "hdf_head_bwd: V too large");
   const long long total = (long long)N * V;
-  int chunks = (int)((total + 2047) / 2048);
-  if (chunks > 148 * 4) chunks = 148 * 4;
-  const int rpc = cdiv(total, chunks);
-  chunks = cdiv(total, rpc);
+  int cpn = head_chunks_per_n(N, V);
+  const int rpc = cdiv(V, cpn);
+  cpn = cdiv(V, rpc);
+  const int chunks = cpn * N;
   HDF_DISPATCH_DTYPE(dtype, T, {
     {
       const bool vecw = can_vec<T>(a, lda, C);
@@ -830,8 +1128,9 @@ int hdf_head_bwd(int dtype, const void* g, const void* a, long long lda, const f
       HDF_VEC_DISPATCH(vecw, {
         const int lanes = 256 / (C / VEC);
         const size_t smem = (size_t)lanes * ncls * (C + 1) * sizeof(float);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(head_wgrad_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        head_wgrad_kernel<T, VEC><<<chunks, 256, smem, s>>>((const T*)g, (const T*)a, lda, V, C, ncls, total, rpc, (float*)workspace);
+        if (ncls <= 2) launch_head_wgrad<T, VEC, 2>(dim3(cpn, N), smem, s, (const T*)g, (const T*)a, lda, (int)V, C, ncls, rpc, (float*)workspace);
+        else if (ncls <= 4) launch_head_wgrad<T, VEC, 4>(dim3(cpn, N), smem, s, (const T*)g, (const T*)a, lda, (int)V, C, ncls, rpc, (float*)workspace);
+        else launch_head_wgrad<T, VEC, 8>(dim3(cpn, N), smem, s, (const T*)g, (const T*)a, lda, (int)V, C, ncls, rpc, (float*)workspace);
       });
     }
     HDF_LAUNCH_CHECK("hdf_head_bwd/wgrad");
@@ -839,7 +1138,16 @@ int hdf_head_bwd(int dtype, const void* g, const void* a, long long lda, const f
     HDF_LAUNCH_CHECK("hdf_head_bwd/finalize");
     const bool vec = can_vec<T>(da, ldd, C);
     const size_t smem2 = (size_t)ncls * C * sizeof(float);
-    HDF_VEC_DISPATCH(vec, { head_dgrad_kernel<T, VEC><<<grid_for(total, 128), 128, smem2, s>>>((const T*)g, w, (T*)da, ldd, V, C, ncls, accumulate_da, total); });
+    HDF_VEC_DISPATCH(vec, {
+      if (vec && sizeof(T) == 2 && fast_ok(C, VEC, V)) {
+        const int rpb = fast_rows_per_block(V, N, 256 / (C / VEC));
+        const dim3 gr((unsigned)cdiv(V, rpb), N);
+        if (ncls <= 2) head_dgrad_fast_kernel<T, VEC, 2><<<gr, 256, 0, s>>>((const T*)g, w, (T*)da, ldd, (int)V, C, ncls, accumulate_da, rpb);
+        else if (ncls <= 4) head_dgrad_fast_kernel<T, VEC, 4><<<gr, 256, 0, s>>>((const T*)g, w, (T*)da, ldd, (int)V, C, ncls, accumulate_da, rpb);
+        else head_dgrad_fast_kernel<T, VEC, 8><<<gr, 256, 0, s>>>((const T*)g, w, (T*)da, ldd, (int)V, C, ncls, accumulate_da, rpb);
+      } else {
+        head_dgrad_kernel<T, VEC><<<grid_for(total, 128), 128, smem2, s>>>((const T*)g, w, (T*)da, ldd, V, C, ncls, accumulate_da, total);
+      } });
   });
   HDF_LAUNCH_CHECK("hdf_head_bwd/dgrad");
   return HDF_OK;

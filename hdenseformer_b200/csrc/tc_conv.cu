@@ -512,10 +512,11 @@ struct TcWgradParams {
   int CWn, nsub_b;
   int a_stages;
   int a_scale;             // 1: A-side coords j + (k-1); 2: A-side is the 2x-resolution tensor, coords 2j + (k-1)
+  int ntaps;               // 27, or 1 for the stem's im2col'ed operand (a single unshifted "tap")
   uint32_t a_sub_bytes, a_stage_bytes, b_sub_bytes, b_stage_bytes;
   uint32_t a_layout, a_sbo, b_layout, b_sbo;
   uint32_t tmem_cols;
-  float* partial;          // [num_slabs][27][Cin][Cout]
+  float* partial;          // [num_slabs][ntaps][Cin][Cout]
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -579,7 +580,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           for (int j = 0; j < nsub; ++j) {
             const int u = u0 + j;
             const int tap = u / p.sub_per_tap, ch0 = (u - tap * p.sub_per_tap) * p.CW;
-            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+            const int kd = p.ntaps == 1 ? 1 : tap / 9, kh = p.ntaps == 1 ? 1 : (tap / 3) % 3, kw = p.ntaps == 1 ? 1 : tap % 3;
             tma_load_5d(smem_base + s * p.a_stage_bytes + j * p.a_sub_bytes, &tmx, afull(s), ch0, aw0 + kw, ah0 + kh, ad0 + kd, n);
           }
           if (++s == p.a_stages) { s = 0; ph ^= 1u; }
@@ -633,7 +634,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       const bool valid = u < p.total_sub;
       const int tap = valid ? u / p.sub_per_tap : 0;
       const int ci = valid ? (u - tap * p.sub_per_tap) * p.CW + m % p.CW : 0;
-      float* dst = p.partial + (((long long)slab * 27 + tap) * p.Cin + ci) * p.Cout;
+      float* dst = p.partial + (((long long)slab * p.ntaps + tap) * p.Cin + ci) * p.Cout;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_begin) * p.Cout);
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         uint32_t v[16];
@@ -946,6 +947,72 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
   }
 }
 
+// ----------------------------------------------------------------------------- stem (first conv, 1..4 input channels)
+// The first layer has only M = 1..4 input channels (block_1_1_left, SURVEY 8d: AI 51, bandwidth-bound).  Zero-padding it
+// to 16 channels costs 9 MMAs with 32-byte rows per 128 voxels (the slowest UMMA operand shape, profiles/r1_umma_probe.txt)
+// and 27 shifted box loads in the weight gradient.  Instead the 27*M taps are gathered once per step into a K-major
+// matrix Xcol [N*V, Kp] (Kp = 27*M rounded up to 64, bf16): forward = one 128B-swizzled box + Kp/16 MMAs per tile,
+// weight gradient = one unshifted operand pair per voxel chunk (Xcol is kept for the backward pass).
+// block = one (n, d, h) output line.  Phase 1 stages the 9 (kd,kh) input lines of every channel in shared memory
+// (coalesced float loads, zero halo / out-of-range lines); phase 2 assembles the W output rows from shared memory with
+// consecutive threads writing consecutive 16-byte chunks of a row (fully coalesced 2*Kp-byte rows).
+template <int CIN>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ out, int D, int H, int W,
+                                                         int Kp) {
+  extern __shared__ float lines[];            // [9*CIN][W+2]
+  int line = blockIdx.x;
+  const int h = line % H; line /= H;
+  const int d = line % D;
+  const long long n = line / D;
+  const long long V = (long long)D * H * W;
+  const float* xn = x + n * CIN * V;
+  const int Wp = W + 2;
+  for (int i = threadIdx.x; i < 9 * CIN * Wp; i += blockDim.x) {
+    const int l = i / Wp, col = i - l * Wp - 1;
+    const int t9 = l / CIN, ci = l - t9 * CIN;
+    const int dd = d + t9 / 3 - 1, hh = h + t9 % 3 - 1;
+    const bool ok = (unsigned)dd < (unsigned)D && (unsigned)hh < (unsigned)H && (unsigned)col < (unsigned)W;
+    lines[i] = ok ? xn[ci * V + ((long long)dd * H + hh) * W + col] : 0.f;
+  }
+  __syncthreads();
+  const int cpr = Kp / 8;
+  bf16* orow = out + ((long long)blockIdx.x * W) * Kp;
+  for (int i = threadIdx.x; i < W * cpr; i += blockDim.x) {
+    const int w = i / cpr, k0 = (i - w * cpr) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      const int tap = k / CIN, ci = k - tap * CIN;
+      const int t9 = tap / 3, kw = tap - t9 * 3;
+      v[j] = tap < 27 ? lines[(t9 * CIN + ci) * Wp + w + kw] : 0.f;
+    }
+    store8<bf16>(orow + (long long)i * 8, v);
+  }
+}
+
+// packed[co][k = tap*Cin + ci] (bf16, zero for k >= 27*Cin) from the torch weight [Cout][Cin][27]
+__global__ void stem_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cin, int Cout, int Kp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * Kp) return;
+  const int co = i / Kp, k = i % Kp;
+  const int tap = k / Cin, ci = k % Cin;
+  out[i] = __float2bfloat16_rn(tap < 27 ? w[((long long)co * Cin + ci) * 27 + tap] : 0.f);
+}
+
+// partial [S][Kp][Cout] -> dw [Cout][Cin][27]
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ g, int S, int Cin, int Cout, int Kp,
+                                         int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 27 * Cin * Cout) return;
+  const int co = i % Cout, k = i / Cout;
+  const int tap = k / Cin, ci = k % Cin;
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += part[((long long)z * Kp + k) * Cout + co];
+  float* q = g + ((long long)co * Cin + ci) * 27 + tap;
+  *q = accumulate ? (*q + s) : s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -971,12 +1038,21 @@ int hdf_tc_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, lo
   return HDF_OK;
 }
 
+// mode 3 (internal, stem path): 1x1x1 "conv" over an im2col'ed tensor [N, D, H, W, Cin = Kp]; weights [Cout][Kp]
+static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y,
+                              long long ldy, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* stream);
+
 int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y,
                       long long ldy, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* stream) {
   if (!hdf_tc_supported(mode, Cin, Cout)) {
     hdf_set_error("hdf_tc_conv3d_fwd: unsupported channels Cin=%d Cout=%d", Cin, Cout);
     return HDF_ERR_UNSUPPORTED;
   }
+  return tc_conv_fwd_launch(mode, x, ldx, w_packed_bf16, bias, y, ldy, N, Do, Ho, Wo, Cin, Cout, stream);
+}
+
+static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y,
+                              long long ldy, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* stream) {
   HDF_REQUIRE(x && w_packed_bf16 && y, "hdf_tc_conv3d_fwd: null pointer");
   HDF_REQUIRE((ldx % 8 == 0) && (ldy % 8 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0),
               "hdf_tc_conv3d_fwd: operands must be 16-byte aligned with channel strides multiple of 8");
@@ -1001,7 +1077,12 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
   p.sbo = 8u * inner;
 
   // ---- plain plan: one TMA box + one MMA group per tap
-  build_taps(mode, p.taps);
+  if (mode == 3) {
+    memset(&p.taps, 0, sizeof(p.taps));
+    p.taps.ncls = 1; p.taps.first[0] = 0; p.taps.first[1] = 1;      // one tap, no shift
+  } else {
+    build_taps(mode, p.taps);
+  }
   pick_tile(D, H, W, p.TD, p.TH, p.TW);
   p.TWstep = p.TW;
   p.nTd = cdiv(D, p.TD); p.nTh = cdiv(H, p.TH); p.nTw = cdiv(W, p.TW);
@@ -1093,7 +1174,7 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
     if (r != CUDA_SUCCESS) { hdf_set_error("hdf_tc_conv3d_fwd: encode(x) failed: %d", (int)r); return HDF_ERR_CUDA; }
   }
   {
-    cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
+    cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)(mode == 3 ? 1 : 27) * Cout};
     cuuint64_t gstr[1] = {(cuuint64_t)Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)p.Nmma};
     cuuint32_t estr[2] = {1, 1};
@@ -1138,8 +1219,10 @@ int hdf_tc_wgrad_supported(int mode, int Cin, int Cout) {
   return wgrad_ok(Cin) && wgrad_ok(Cout) && (mode == 0 ? Cout : Cin) <= 256;
 }
 
-static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradParams& p) {
+static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradParams& p, int ntaps = 27) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.ntaps = ntaps;
+  p.a_scale = 1;
   p.KV = (Cout > 128) ? 64 : 128;
   // tile = KV voxels
   {
@@ -1156,7 +1239,7 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   p.CW = Cin < 64 ? Cin : 64;
   p.SPG = 128 / p.CW;
   p.sub_per_tap = Cin / p.CW;
-  p.total_sub = 27 * p.sub_per_tap;
+  p.total_sub = ntaps * p.sub_per_tap;
   p.total_groups = cdiv(p.total_sub, p.SPG);
   p.groups_per_pass = 512 / Cout;
   if (p.groups_per_pass > p.total_groups) p.groups_per_pass = p.total_groups;
@@ -1392,6 +1475,98 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
   tc_wgrad_reduce_kernel<<<min(2048, cdiv(per, 256)), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, p.num_slabs,
                                                                                      Ca, Cb, sa, sb, accumulate, swap ? 1 : 0);
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad/reduce");
+  return HDF_OK;
+}
+
+
+// ---- stem path (see stem_im2col_kernel)
+int hdf_stem_kp(int Cin) { return (Cin >= 1 && Cin <= 4) ? (27 * Cin + 63) / 64 * 64 : 0; }
+
+int hdf_stem_supported(int Cin, int Cout) { return hdf_stem_kp(Cin) > 0 && (Cout == 16 || Cout == 32 || Cout == 64); }
+
+int hdf_stem_im2col(const float* x_ncdhw, void* xcol_bf16, int N, int Cin, int D, int H, int W, void* stream) {
+  HDF_REQUIRE(x_ncdhw && xcol_bf16 && hdf_stem_kp(Cin) > 0, "hdf_stem_im2col: bad args (Cin must be 1..4)");
+  const int Kp = hdf_stem_kp(Cin);
+  const unsigned grid = (unsigned)((long long)N * D * H);
+  const size_t smem = (size_t)9 * Cin * (W + 2) * sizeof(float);
+  HDF_REQUIRE(smem <= 200 * 1024, "hdf_stem_im2col: W=%d too large", W);
+  cudaStream_t s = (cudaStream_t)stream;
+#define HDF_STEM_IM2COL(CI)                                                                                              \
+  {                                                                                                                      \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(stem_im2col_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    stem_im2col_kernel<CI><<<grid, 256, smem, s>>>(x_ncdhw, (bf16*)xcol_bf16, D, H, W, Kp);                               \
+  }
+  switch (Cin) {
+    case 1: HDF_STEM_IM2COL(1) break;
+    case 2: HDF_STEM_IM2COL(2) break;
+    case 3: HDF_STEM_IM2COL(3) break;
+    default: HDF_STEM_IM2COL(4) break;
+  }
+#undef HDF_STEM_IM2COL
+  HDF_LAUNCH_CHECK("hdf_stem_im2col");
+  return HDF_OK;
+}
+
+int hdf_stem_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, void* stream) {
+  HDF_REQUIRE(w && packed_bf16 && hdf_stem_kp(Cin) > 0, "hdf_stem_pack_weights: bad args");
+  const int Kp = hdf_stem_kp(Cin);
+  stem_pack_kernel<<<cdiv((long long)Cout * Kp, 256), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)packed_bf16, Cin, Cout, Kp);
+  HDF_LAUNCH_CHECK("hdf_stem_pack_weights");
+  return HDF_OK;
+}
+
+int hdf_stem_conv_fwd(const void* xcol_bf16, const void* w_packed_bf16, void* y, long long ldy, int N, int D, int H, int W,
+                      int Cin, int Cout, void* stream) {
+  HDF_REQUIRE(hdf_stem_supported(Cin, Cout), "hdf_stem_conv_fwd: unsupported Cin=%d Cout=%d", Cin, Cout);
+  const int Kp = hdf_stem_kp(Cin);
+  return tc_conv_fwd_launch(3, xcol_bf16, Kp, w_packed_bf16, nullptr, y, ldy, N, D, H, W, Kp, Cout, stream);
+}
+
+size_t hdf_stem_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout) {
+  if (!hdf_stem_supported(Cin, Cout)) return 0;
+  TcWgradParams p;
+  tc_wgrad_plan(N, D, H, W, hdf_stem_kp(Cin), Cout, p, 1);
+  return (size_t)p.num_slabs * hdf_stem_kp(Cin) * Cout * sizeof(float);
+}
+
+// dw [Cout][Cin][27] (+)= sum_v dy[v][co] * xcol[v][tap*Cin + ci]
+int hdf_stem_conv_wgrad(const void* xcol_bf16, const void* dy, long long ldy, float* dw, int N, int D, int H, int W, int Cin,
+                        int Cout, void* workspace, size_t ws_bytes, int accumulate, void* stream) {
+  HDF_REQUIRE(hdf_stem_supported(Cin, Cout), "hdf_stem_conv_wgrad: unsupported Cin=%d Cout=%d", Cin, Cout);
+  HDF_REQUIRE(xcol_bf16 && dy && dw && workspace && (ldy % 8 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)xcol_bf16 % 16 == 0),
+              "hdf_stem_conv_wgrad: bad args");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { hdf_set_error("hdf_stem_conv_wgrad: cuTensorMapEncodeTiled unavailable"); return HDF_ERR_CUDA; }
+  const int Kp = hdf_stem_kp(Cin);
+  TcWgradParams p;
+  const int passes = tc_wgrad_plan(N, D, H, W, Kp, Cout, p, 1);
+  HDF_REQUIRE(ws_bytes >= (size_t)p.num_slabs * Kp * Cout * sizeof(float), "hdf_stem_conv_wgrad: workspace too small");
+  p.partial = (float*)workspace;
+  CUtensorMap tmx, tmdy;
+  for (int which = 0; which < 2; ++which) {
+    const void* base = which == 0 ? xcol_bf16 : dy;
+    const long long ld = which == 0 ? Kp : ldy;
+    const int C = which == 0 ? Kp : Cout;
+    const int cw = which == 0 ? p.CW : p.CWn;
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+    cuuint64_t gstr[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2, (cuuint64_t)D * H * W * ld * 2};
+    cuuint32_t box[5] = {(cuuint32_t)cw, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TD, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(which == 0 ? &tmx : &tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { hdf_set_error("hdf_stem_conv_wgrad: encode failed: %d", (int)r); return HDF_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + 2 * (size_t)p.b_stage_bytes + 1024 + 8 * (2 * p.a_stages + 6) + 16;
+  cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e != cudaSuccess) { hdf_set_error("hdf_stem_conv_wgrad: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
+  HDF_REQUIRE(smem <= 227 * 1024, "hdf_stem_conv_wgrad: smem plan too large (%zu)", smem);
+  dim3 grid(p.num_slabs, passes);
+  tc_conv_wgrad_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmdy, p);
+  HDF_LAUNCH_CHECK("hdf_stem_conv_wgrad");
+  stem_wgrad_reduce_kernel<<<cdiv(27ll * Cin * Cout, 128), 128, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, p.num_slabs,
+                                                                                          Cin, Cout, Kp, accumulate);
+  HDF_LAUNCH_CHECK("hdf_stem_conv_wgrad/reduce");
   return HDF_OK;
 }
 

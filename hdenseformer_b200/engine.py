@@ -87,6 +87,7 @@ class Engine:
         # tensor-core work is available to overlap the branch's long chain of small, latency-bound kernels.
         self.defer_wgrad = os.environ.get("HDF_NO_DEFER_WGRAD") is None
         self._deferred = []
+        self.use_stem = os.environ.get("HDF_NO_STEM") is None   # im2col + GEMM first layer (bf16 tensor-core path only)
         self.fused_dct = True     # fused post-attention chain kernels (csrc/dct.cu) instead of ~40 single-op launches
         # fused layer-head kernels (Linear_l + LN1 + to_qkv): measured slower than the three single-op launches on B200
         # (34.2 vs 33.1 ms/step), so they stay opt-in
@@ -107,7 +108,9 @@ class Engine:
         """x: [N,D,H,W,Cin] view; w: torch-layout weight; out: [N,Do,Ho,Wo,Cout] view."""
         if mode == 0:    # Conv3d weight [Cout, Cin, 27]
             Cout, Cin = w.shape[0], w.shape[1]
-            Cx = x.shape[-1]     # > Cin when the input was zero-padded to 16 channels (first layer)
+            Cx = x.shape[-1]     # > Cin for the first layer: im2col'ed (stem) or zero-padded to 16 channels
+            if Cx != Cin and Cx == ops.stem_kp(Cin):
+                return ops.stem_conv_fwd(x, w, out)
             if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(0, Cx, Cout):
                 return ops.tc_conv3d_fwd(x, ops.tc_pack(w, Cx, Cout, 27, Cin * 27, False, cin_valid=Cin), bias, out)
             assert Cx == Cin
@@ -140,6 +143,8 @@ class Engine:
         if mode == 0:    # dw [Cout, Cin, 27]
             Cout, Cin = dw.shape[0], dw.shape[1]
             Cx = x.shape[-1]
+            if Cx != Cin and Cx == ops.stem_kp(Cin):
+                return ops.stem_conv_wgrad(x, dy, dw)
             if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_wgrad_supported(0, Cx, Cout):
                 if Cx == Cin:
                     return ops.tc_conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
@@ -426,8 +431,11 @@ class Engine:
             return at3
 
         # ---------------- encoder; skip tensors are written straight into the decoder concat buffers
-        pad = 16 if (self.use_tc and dtype == torch.bfloat16 and M < 16 and ops.tc_supported(0, 16, nf)) else 0
-        xcl = ops.ncdhw_to_cl(x, dtype, pad_to=pad)
+        if self.use_tc and self.use_stem and dtype == torch.bfloat16 and ops.stem_supported(M, nf):
+            xcl = ops.stem_im2col(x)        # first conv = one GEMM over the gathered taps (csrc/tc_conv.cu, stem path)
+        else:
+            pad = 16 if (self.use_tc and dtype == torch.bfloat16 and M < 16 and ops.tc_supported(0, 16, nf)) else 0
+            xcl = ops.ncdhw_to_cl(x, dtype, pad_to=pad)
         c.xcl = xcl
         cat1 = empty((B, D, H, W, 2 * nf))
         cat2 = empty((B, D // 2, H // 2, W // 2, 4 * nf))

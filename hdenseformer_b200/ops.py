@@ -117,6 +117,42 @@ def tc_conv3d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, stride_
                                         Cout, _p(ws), ws.numel(), int(accumulate), _s()), "tc_conv3d_wgrad")
 
 
+# ----------------------------------------------------------------------------- stem (first conv through im2col + GEMM)
+def stem_kp(Cin: int) -> int:
+    return int(_lib().hdf_stem_kp(Cin))
+
+
+def stem_supported(Cin: int, Cout: int) -> bool:
+    return bool(_lib().hdf_stem_supported(Cin, Cout))
+
+
+def stem_im2col(x: torch.Tensor) -> torch.Tensor:
+    """x: NCDHW fp32 -> xcol [N, D, H, W, Kp] bf16 (k = tap*Cin + ci, zero padded)"""
+    N, Cin, D, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty((N, D, H, W, stem_kp(Cin)), dtype=torch.bfloat16, device=x.device)
+    _C.check(_lib().hdf_stem_im2col(_p(x), _p(out), N, Cin, D, H, W, _s()), "stem_im2col")
+    return out
+
+
+def stem_conv_fwd(xcol: torch.Tensor, w: torch.Tensor, out: torch.Tensor):
+    """w: torch Conv3d weight [Cout, Cin, 3, 3, 3]; out: [N, D, H, W, Cout] bf16 view"""
+    N, D, H, W, Cout = out.shape
+    Cin = w.shape[1]
+    wp = torch.empty((Cout, xcol.shape[-1]), dtype=torch.bfloat16, device=w.device)
+    _C.check(_lib().hdf_stem_pack_weights(_p(w), _p(wp), Cin, Cout, _s()), "stem_pack_weights")
+    _C.check(_lib().hdf_stem_conv_fwd(_p(xcol), _p(wp), _p(out), _ld(out), N, D, H, W, Cin, Cout, _s()), "stem_conv_fwd")
+    return out
+
+
+def stem_conv_wgrad(xcol: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, accumulate=False):
+    N, D, H, W, Cout = dy.shape
+    Cin = dw.shape[1]
+    ws = Workspace.get(_lib().hdf_stem_wgrad_workspace(N, D, H, W, Cin, Cout))
+    _C.check(_lib().hdf_stem_conv_wgrad(_p(xcol), _p(dy), _ld(dy), _p(dw), N, D, H, W, Cin, Cout, _p(ws), ws.numel(),
+                                        int(accumulate), _s()), "stem_conv_wgrad")
+
+
 # ----------------------------------------------------------------------------- instance norm & friends
 def instnorm_stats(y: torch.Tensor, eps: float = 1e-5):
     N, C = y.shape[0], y.shape[-1]

@@ -61,6 +61,20 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
                         long long stride_co, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* workspace,
                         size_t ws_bytes, int accumulate, void* stream);
 
+/* ---- stem: the network's first BasicConv3d conv (models/HDenseFormer.py:198, Conv3d(in_channels -> nf, k3 p1, no bias),
+ *      in_channels = 1..4).  The 27*Cin taps of every voxel are gathered once into a K-major bf16 matrix
+ *      xcol [N*D*H*W, Kp] (Kp = hdf_stem_kp(Cin) = 27*Cin rounded up to 64, zero padded) straight from the caller's
+ *      NCDHW fp32 batch; forward is then one tcgen05 GEMM over xcol, the weight gradient one over (xcol, dy). ---- */
+int hdf_stem_kp(int Cin);                       /* 0 when unsupported */
+int hdf_stem_supported(int Cin, int Cout);
+int hdf_stem_im2col(const float* x_ncdhw, void* xcol_bf16, int N, int Cin, int D, int H, int W, void* stream);
+int hdf_stem_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, void* stream); /* [Cout][Kp] bf16 from [Cout][Cin][27] */
+int hdf_stem_conv_fwd(const void* xcol_bf16, const void* w_packed_bf16, void* y, long long ldy, int N, int D, int H, int W,
+                      int Cin, int Cout, void* stream);
+size_t hdf_stem_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout);
+int hdf_stem_conv_wgrad(const void* xcol_bf16, const void* dy, long long ldy, float* dw, int N, int D, int H, int W, int Cin,
+                        int Cout, void* workspace, size_t ws_bytes, int accumulate, void* stream);
+
 /* ---- patch embedding (nn.Conv3d k16 s16 + position_embeddings + Dropout: models/HDenseFormer.py:115-119,
  *      133-138).  img is the caller's NCDHW fp32 batch; tokens are [B*ntok, E] fp32 rows (ld = ldo). ---- */
 size_t hdf_patch_embed_fwd_workspace(int B, int D, int H, int W, int E);

@@ -172,3 +172,41 @@ def test_tc_first_layer_zero_padded_channels():
     dw = tmp[:, :54].reshape(32, 2, 3, 3, 3)
     assert ((dw - wq.grad).abs().max() / wq.grad.abs().max()).item() < 1e-3
     assert tmp[:, 54:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("cin,cout,size,N", [(2, 32, (16, 16, 16), 2), (1, 16, (8, 12, 20), 1), (3, 32, (16, 24, 40), 1),
+                                             (4, 32, (12, 20, 18), 2), (2, 64, (9, 10, 11), 1)])
+def test_stem_im2col_gemm_matches_torch(cin, cout, size, N):
+    """First conv (1..4 input channels) through the im2col + tcgen05 GEMM stem path: gathered matrix is exact,
+    forward and weight gradient against torch's fp32 conv on the bf16-rounded operands."""
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    assert ops.stem_supported(cin, cout)
+    torch.manual_seed(cin * 7 + cout)
+    x = torch.randn(N, cin, *size, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, 3, device=DEV) / math.sqrt(27 * cin)
+    xcol = ops.stem_im2col(x)
+    Kp = ops.stem_kp(cin)
+    assert Kp % 64 == 0 and tuple(xcol.shape) == (N, *size, Kp)
+    # the gathered matrix equals torch's unfold of the zero-padded, bf16-rounded input, k = tap*Cin + ci
+    xq = x.to(torch.bfloat16).float()
+    xp = F.pad(xq, (1, 1, 1, 1, 1, 1))
+    D, H, W = size
+    cols = []
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                cols.append(xp[:, :, kd:kd + D, kh:kh + H, kw:kw + W])      # [N, cin, D, H, W]
+    ref_col = torch.stack(cols, dim=1).permute(0, 3, 4, 5, 1, 2).reshape(N, D, H, W, 27 * cin)
+    assert torch.equal(xcol[..., :27 * cin].float(), ref_col)
+    assert xcol[..., 27 * cin:].abs().max().item() == 0
+    y = torch.empty(N, *size, cout + 8, dtype=torch.bfloat16, device=DEV)[..., :cout]   # channel-slice output
+    ops.stem_conv_fwd(xcol, w, y)
+    wq = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv3d(xq, wq, None, padding=1)
+    refl = ref.detach().permute(0, 2, 3, 4, 1)
+    assert ((y.float() - refl).abs().max() / refl.abs().max()).item() < 1e-2
+    g = torch.randn(N, *size, cout, device=DEV).to(torch.bfloat16)
+    ref.backward(g.float().permute(0, 4, 1, 2, 3))
+    dw = torch.full((cout, cin, 3, 3, 3), 7.0, device=DEV)
+    ops.stem_conv_wgrad(xcol, g, dw)
+    assert ((dw - wq.grad).abs().max() / wq.grad.abs().max()).item() < 1e-3
