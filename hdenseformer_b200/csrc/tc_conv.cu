@@ -967,26 +967,47 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   const long long V = (long long)D * H * W;
   const float* xn = x + n * CIN * V;
   const int Wp = W + 2;
-  for (int i = threadIdx.x; i < 9 * CIN * Wp; i += blockDim.x) {
-    const int l = i / Wp, col = i - l * Wp - 1;
+  // one warp per staged line (no per-element index division), up to 8 independent loads in flight per lane
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int l = warp; l < 9 * CIN; l += nwarps) {
     const int t9 = l / CIN, ci = l - t9 * CIN;
     const int dd = d + t9 / 3 - 1, hh = h + t9 % 3 - 1;
-    const bool ok = (unsigned)dd < (unsigned)D && (unsigned)hh < (unsigned)H && (unsigned)col < (unsigned)W;
-    lines[i] = ok ? xn[ci * V + ((long long)dd * H + hh) * W + col] : 0.f;
+    const bool okl = (unsigned)dd < (unsigned)D && (unsigned)hh < (unsigned)H;
+    const float* src = xn + ci * V + ((long long)dd * H + hh) * W - 1;     // src[p] = input column p-1
+    float* dst = lines + l * Wp;
+    for (int p0 = lane; p0 < Wp; p0 += 256) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int pcol = p0 + u * 32;
+        v[u] = (okl && pcol >= 1 && pcol <= W) ? src[pcol] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int pcol = p0 + u * 32;
+        if (pcol < Wp) dst[pcol] = v[u];
+      }
+    }
   }
   __syncthreads();
+  // 256 % (Kp/8) == 0: a thread keeps the same 16-byte chunk of the row for all its items, so the tap decode of its
+  // 8 k's is done once (the kernel was issue-bound when it decoded per element)
   const int cpr = Kp / 8;
+  const int k0 = (threadIdx.x % cpr) * 8;
+  int off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k0 + j;
+    const int tap = k / CIN, ci = k - tap * CIN;
+    const int t9 = tap / 3, kw = tap - t9 * 3;
+    off[j] = tap < 27 ? (t9 * CIN + ci) * Wp + kw : -1;
+  }
   bf16* orow = out + ((long long)blockIdx.x * W) * Kp;
   for (int i = threadIdx.x; i < W * cpr; i += blockDim.x) {
-    const int w = i / cpr, k0 = (i - w * cpr) * 8;
+    const int w = i / cpr;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = k0 + j;
-      const int tap = k / CIN, ci = k - tap * CIN;
-      const int t9 = tap / 3, kw = tap - t9 * 3;
-      v[j] = tap < 27 ? lines[(t9 * CIN + ci) * Wp + w + kw] : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? lines[off[j] + w] : 0.f;
     store8<bf16>(orow + (long long)i * 8, v);
   }
 }

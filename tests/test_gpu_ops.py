@@ -346,3 +346,18 @@ def test_fused_dct_head_matches_unfused_composition():
         assert torch.equal(dF_f[:, Cl:], base[:, Cl:])
         for k in P:
             assert rel(Gf[k], Gu[k]) < 1e-4, k
+
+
+def test_upsample_cell_kernel_odd_sizes_and_channel_slices():
+    """bf16 cell-centred trilinear x2 (csrc/glue.cu): odd spatial sizes, size-1 dims (all-clamped cells), input and output
+    as channel slices of wider buffers."""
+    torch.manual_seed(11)
+    for size, C in [((3, 5, 7), 32), ((1, 1, 9), 16), ((2, 9, 1), 64)]:
+        x = torch.randn(2, *size, C + 16, device=DEV).to(torch.bfloat16)
+        xs = x[..., 8:8 + C]
+        ref = F.interpolate(xs.float().permute(0, 4, 1, 2, 3), scale_factor=2, mode="trilinear", align_corners=False)
+        buf = torch.full((2, 2 * size[0], 2 * size[1], 2 * size[2], C + 8), 5.0, dtype=torch.bfloat16, device=DEV)
+        ops.upsample2_fwd(xs, buf[..., :C])
+        got = buf[..., :C].float().permute(0, 4, 1, 2, 3)
+        assert rel(got, ref) < TOL[torch.bfloat16]
+        assert (buf[..., C:] == 5.0).all()
