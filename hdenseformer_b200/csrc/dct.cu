@@ -84,59 +84,106 @@ __global__ void ln_param_finalize_kernel(const float* __restrict__ partial, int 
 // ---------------------------------------------------------------------------
 // attention, heads*4 = inner dim.  qkv rows: [q(inner) | k(inner) | v(inner)]
 // ---------------------------------------------------------------------------
-constexpr int AT = 128;  // queries per block == keys per smem tile
+// Attention (models/HDenseFormer.py:47-75): 8 heads of dim 4, N = 729 tokens at 144^3: tiny in FLOPs, long in dependent
+// latency.  A query (key, for dk/dv) is owned by AP = 8 adjacent lanes that each walk every 8th key of the shared-memory
+// tile and are merged with shuffles, so the serial loop per thread is N/8 long and the grid has 8x more threads than
+// rows (B*H*N = 11.6 k rows would otherwise fill 4 % of the GPU); the forward rescales its running max once per tile
+// (16 independent exponentials per thread per tile) instead of once per key.
+constexpr int AT = 128;  // keys (queries for dk/dv) per shared-memory tile == threads per block
+constexpr int AP = 8;    // lanes per owner row
+constexpr int AQ = AT / AP;   // owner rows per block
+constexpr int AU = AT / AP;   // tile rows walked per lane
 
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+// T = keys staged per pass (multiple of AT, <= 1024: all 729 tokens of the headline config in ONE global round trip;
+// next to the persistent convolution kernels each dependent trip to global memory costs microseconds)
 __global__ void __launch_bounds__(AT) attn_fwd_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ o,
-                                                     long long ldo, float* __restrict__ lse, int N, int H, float scale) {
-  __shared__ float4 sk[AT], sv[AT];
+                                                     long long ldo, float* __restrict__ lse, int N, int H, float scale, int T) {
+  extern __shared__ float4 asm4[];
+  float4* sk = asm4;
+  float4* sv = asm4 + T;
   const int h = blockIdx.y, b = blockIdx.z;
   const int inner = 4 * H;
-  const int i = blockIdx.x * AT + threadIdx.x;
+  const int part = threadIdx.x % AP;
+  const int i = blockIdx.x * AQ + threadIdx.x / AP;
   const float* base = qkv + (long long)b * N * ld;
   float4 q = make_float4(0, 0, 0, 0);
   if (i < N) q = *reinterpret_cast<const float4*>(base + (long long)i * ld + 4 * h);
   q.x *= scale; q.y *= scale; q.z *= scale; q.w *= scale;
   float m = -INFINITY, l = 0.f;
   float4 acc = make_float4(0, 0, 0, 0);
-  for (int j0 = 0; j0 < N; j0 += AT) {
-    const int j = j0 + threadIdx.x;
-    if (j < N) {
-      sk[threadIdx.x] = *reinterpret_cast<const float4*>(base + (long long)j * ld + inner + 4 * h);
-      sv[threadIdx.x] = *reinterpret_cast<const float4*>(base + (long long)j * ld + 2 * inner + 4 * h);
+  for (int j0 = 0; j0 < N; j0 += T) {
+    for (int t = threadIdx.x; t < T; t += AT) {
+      const int j = j0 + t;
+      if (j < N) {
+        sk[t] = *reinterpret_cast<const float4*>(base + (long long)j * ld + inner + 4 * h);
+        sv[t] = *reinterpret_cast<const float4*>(base + (long long)j * ld + 2 * inner + 4 * h);
+      }
     }
     __syncthreads();
-    const int cnt = min(AT, N - j0);
-    for (int t = 0; t < cnt; ++t) {
-      const float4 k = sk[t], v = sv[t];
-      const float s = q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w;
-      if (s > m) {
-        const float r = __expf(m - s);
-        l *= r; acc.x *= r; acc.y *= r; acc.z *= r; acc.w *= r;
-        m = s;
+    const int tcnt = min(T, N - j0);
+    for (int g0 = 0; g0 < tcnt; g0 += AT) {
+      const int cnt = min(AT, tcnt - g0);
+      float sc[AU];
+      float mt = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < AU; ++u) {
+        const int t = part + u * AP;
+        sc[u] = t < cnt ? dot4(q, sk[g0 + t]) : -INFINITY;
+        mt = fmaxf(mt, sc[u]);
       }
-      const float p = __expf(s - m);
-      l += p;
-      acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y); acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+      if (mt > -INFINITY) {
+        const float mn = fmaxf(m, mt);
+        const float r = __expf(m - mn);          // m = -inf on the first group -> 0
+        l *= r; acc.x *= r; acc.y *= r; acc.z *= r; acc.w *= r;
+        m = mn;
+#pragma unroll
+        for (int u = 0; u < AU; ++u) {
+          const int t = part + u * AP;
+          if (t < cnt) {
+            const float pr = __expf(sc[u] - mn);
+            const float4 v = sv[g0 + t];
+            l += pr;
+            acc.x = fmaf(pr, v.x, acc.x); acc.y = fmaf(pr, v.y, acc.y); acc.z = fmaf(pr, v.z, acc.z); acc.w = fmaf(pr, v.w, acc.w);
+          }
+        }
+      }
     }
     __syncthreads();
   }
-  if (i < N) {
+  // merge the 8 partial (m, l, acc) of the row
+  float ma = m;
+  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+  ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 4));
+  const float r = (m > -INFINITY) ? __expf(m - ma) : 0.f;
+  l = group8_sum(l * r);
+  acc.x = group8_sum(acc.x * r); acc.y = group8_sum(acc.y * r); acc.z = group8_sum(acc.z * r); acc.w = group8_sum(acc.w * r);
+  if (i < N && part == 0) {
     const float inv = 1.f / l;
     *reinterpret_cast<float4*>(o + ((long long)b * N + i) * ldo + 4 * h) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-    lse[((long long)b * H + h) * N + i] = m + __logf(l);
+    lse[((long long)b * H + h) * N + i] = ma + __logf(l);
   }
 }
 
-// dq: thread per query
-__global__ void __launch_bounds__(AT) attn_bwd_dq_kernel(const float* __restrict__ qkv, long long ld,
-                                                        const float* __restrict__ o, long long ldo,
-                                                        const float* __restrict__ dout, long long lddo,
-                                                        const float* __restrict__ lse, float* __restrict__ dqkv,
-                                                        long long ldg, int N, int H, float scale) {
-  __shared__ float4 sk[AT], sv[AT];
+// dq: 8 lanes per query
+__device__ __forceinline__ void attn_bwd_dq_body(float4* smem4, int T, int bx, const float* __restrict__ qkv, long long ld,
+                                                 const float* __restrict__ o, long long ldo, const float* __restrict__ dout,
+                                                 long long lddo, const float* __restrict__ lse, float* __restrict__ dqkv,
+                                                 long long ldg, int N, int H, float scale) {
+  float4* sk = smem4;
+  float4* sv = smem4 + T;
   const int h = blockIdx.y, b = blockIdx.z;
   const int inner = 4 * H;
-  const int i = blockIdx.x * AT + threadIdx.x;
+  const int part = threadIdx.x % AP;
+  const int i = bx * AQ + threadIdx.x / AP;
   const float* base = qkv + (long long)b * N * ld;
   float4 q = make_float4(0, 0, 0, 0), dO = q, O = q;
   float L = 0.f;
@@ -146,42 +193,46 @@ __global__ void __launch_bounds__(AT) attn_bwd_dq_kernel(const float* __restrict
     O = *reinterpret_cast<const float4*>(o + ((long long)b * N + i) * ldo + 4 * h);
     L = lse[((long long)b * H + h) * N + i];
   }
-  const float Di = dO.x * O.x + dO.y * O.y + dO.z * O.z + dO.w * O.w;
+  const float Di = dot4(dO, O);
   float4 dq = make_float4(0, 0, 0, 0);
-  for (int j0 = 0; j0 < N; j0 += AT) {
-    const int j = j0 + threadIdx.x;
-    if (j < N) {
-      sk[threadIdx.x] = *reinterpret_cast<const float4*>(base + (long long)j * ld + inner + 4 * h);
-      sv[threadIdx.x] = *reinterpret_cast<const float4*>(base + (long long)j * ld + 2 * inner + 4 * h);
+  for (int j0 = 0; j0 < N; j0 += T) {
+    for (int t = threadIdx.x; t < T; t += AT) {
+      const int j = j0 + t;
+      if (j < N) {
+        sk[t] = *reinterpret_cast<const float4*>(base + (long long)j * ld + inner + 4 * h);
+        sv[t] = *reinterpret_cast<const float4*>(base + (long long)j * ld + 2 * inner + 4 * h);
+      }
     }
     __syncthreads();
-    const int cnt = min(AT, N - j0);
-    for (int t = 0; t < cnt; ++t) {
+    const int tcnt = min(T, N - j0);
+#pragma unroll 4
+    for (int t = part; t < tcnt; t += AP) {
       const float4 k = sk[t], v = sv[t];
-      const float s = scale * (q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w);
-      const float p = __expf(s - L);
-      const float dp = dO.x * v.x + dO.y * v.y + dO.z * v.z + dO.w * v.w;
-      const float ds = p * (dp - Di);
+      const float pr = __expf(scale * dot4(q, k) - L);
+      const float ds = pr * (dot4(dO, v) - Di);
       dq.x = fmaf(ds, k.x, dq.x); dq.y = fmaf(ds, k.y, dq.y); dq.z = fmaf(ds, k.z, dq.z); dq.w = fmaf(ds, k.w, dq.w);
     }
     __syncthreads();
   }
-  if (i < N)
+  dq.x = group8_sum(dq.x); dq.y = group8_sum(dq.y); dq.z = group8_sum(dq.z); dq.w = group8_sum(dq.w);
+  if (i < N && part == 0)
     *reinterpret_cast<float4*>(dqkv + ((long long)b * N + i) * ldg + 4 * h) =
         make_float4(dq.x * scale, dq.y * scale, dq.z * scale, dq.w * scale);
 }
 
-// dk, dv: thread per key
-__global__ void __launch_bounds__(AT) attn_bwd_dkv_kernel(const float* __restrict__ qkv, long long ld,
-                                                         const float* __restrict__ o, long long ldo,
-                                                         const float* __restrict__ dout, long long lddo,
-                                                         const float* __restrict__ lse, float* __restrict__ dqkv,
-                                                         long long ldg, int N, int H, float scale) {
-  __shared__ float4 sq[AT], sdo[AT];
-  __shared__ float sL[AT], sD[AT];
+// dk, dv: 8 lanes per key
+__device__ __forceinline__ void attn_bwd_dkv_body(float4* smem4, int T, int bx, const float* __restrict__ qkv, long long ld,
+                                                  const float* __restrict__ o, long long ldo, const float* __restrict__ dout,
+                                                  long long lddo, const float* __restrict__ lse, float* __restrict__ dqkv,
+                                                  long long ldg, int N, int H, float scale) {
+  float4* sq = smem4;
+  float4* sdo = smem4 + T;
+  float* sL = reinterpret_cast<float*>(smem4 + 2 * T);
+  float* sD = sL + T;
   const int h = blockIdx.y, b = blockIdx.z;
   const int inner = 4 * H;
-  const int j = blockIdx.x * AT + threadIdx.x;
+  const int part = threadIdx.x % AP;
+  const int j = bx * AQ + threadIdx.x / AP;
   const float* base = qkv + (long long)b * N * ld;
   float4 k = make_float4(0, 0, 0, 0), v = k;
   if (j < N) {
@@ -189,35 +240,49 @@ __global__ void __launch_bounds__(AT) attn_bwd_dkv_kernel(const float* __restric
     v = *reinterpret_cast<const float4*>(base + (long long)j * ld + 2 * inner + 4 * h);
   }
   float4 dk = make_float4(0, 0, 0, 0), dv = dk;
-  for (int i0 = 0; i0 < N; i0 += AT) {
-    const int i = i0 + threadIdx.x;
-    if (i < N) {
-      const float4 q = *reinterpret_cast<const float4*>(base + (long long)i * ld + 4 * h);
-      const float4 dO = *reinterpret_cast<const float4*>(dout + ((long long)b * N + i) * lddo + 4 * h);
-      const float4 O = *reinterpret_cast<const float4*>(o + ((long long)b * N + i) * ldo + 4 * h);
-      sq[threadIdx.x] = q;
-      sdo[threadIdx.x] = dO;
-      sL[threadIdx.x] = lse[((long long)b * H + h) * N + i];
-      sD[threadIdx.x] = dO.x * O.x + dO.y * O.y + dO.z * O.z + dO.w * O.w;
+  for (int i0 = 0; i0 < N; i0 += T) {
+    for (int t = threadIdx.x; t < T; t += AT) {
+      const int i = i0 + t;
+      if (i < N) {
+        const float4 q = *reinterpret_cast<const float4*>(base + (long long)i * ld + 4 * h);
+        const float4 dO = *reinterpret_cast<const float4*>(dout + ((long long)b * N + i) * lddo + 4 * h);
+        const float4 O = *reinterpret_cast<const float4*>(o + ((long long)b * N + i) * ldo + 4 * h);
+        sq[t] = q;
+        sdo[t] = dO;
+        sL[t] = lse[((long long)b * H + h) * N + i];
+        sD[t] = dot4(dO, O);
+      }
     }
     __syncthreads();
-    const int cnt = min(AT, N - i0);
-    for (int t = 0; t < cnt; ++t) {
+    const int tcnt = min(T, N - i0);
+#pragma unroll 4
+    for (int t = part; t < tcnt; t += AP) {
       const float4 q = sq[t], dO = sdo[t];
-      const float s = scale * (q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w);
-      const float p = __expf(s - sL[t]);
-      dv.x = fmaf(p, dO.x, dv.x); dv.y = fmaf(p, dO.y, dv.y); dv.z = fmaf(p, dO.z, dv.z); dv.w = fmaf(p, dO.w, dv.w);
-      const float dp = dO.x * v.x + dO.y * v.y + dO.z * v.z + dO.w * v.w;
-      const float ds = p * (dp - sD[t]);
+      const float pr = __expf(scale * dot4(q, k) - sL[t]);
+      dv.x = fmaf(pr, dO.x, dv.x); dv.y = fmaf(pr, dO.y, dv.y); dv.z = fmaf(pr, dO.z, dv.z); dv.w = fmaf(pr, dO.w, dv.w);
+      const float ds = pr * (dot4(dO, v) - sD[t]);
       dk.x = fmaf(ds, q.x, dk.x); dk.y = fmaf(ds, q.y, dk.y); dk.z = fmaf(ds, q.z, dk.z); dk.w = fmaf(ds, q.w, dk.w);
     }
     __syncthreads();
   }
-  if (j < N) {
+  dk.x = group8_sum(dk.x); dk.y = group8_sum(dk.y); dk.z = group8_sum(dk.z); dk.w = group8_sum(dk.w);
+  dv.x = group8_sum(dv.x); dv.y = group8_sum(dv.y); dv.z = group8_sum(dv.z); dv.w = group8_sum(dv.w);
+  if (j < N && part == 0) {
     float* g = dqkv + ((long long)b * N + j) * ldg;
     *reinterpret_cast<float4*>(g + inner + 4 * h) = make_float4(dk.x * scale, dk.y * scale, dk.z * scale, dk.w * scale);
     *reinterpret_cast<float4*>(g + 2 * inner + 4 * h) = dv;
   }
+}
+
+// one launch for both halves of the attention backward: blocks [0, nb) compute dq, blocks [nb, 2nb) compute dk/dv
+__global__ void __launch_bounds__(AT) attn_bwd_kernel(const float* __restrict__ qkv, long long ld, const float* __restrict__ o,
+                                                     long long ldo, const float* __restrict__ dout, long long lddo,
+                                                     const float* __restrict__ lse, float* __restrict__ dqkv, long long ldg,
+                                                     int N, int H, float scale, int T) {
+  extern __shared__ float4 asm4[];
+  const int nb = gridDim.x / 2;
+  if ((int)blockIdx.x < nb) attn_bwd_dq_body(asm4, T, blockIdx.x, qkv, ld, o, ldo, dout, lddo, lse, dqkv, ldg, N, H, scale);
+  else attn_bwd_dkv_body(asm4, T, blockIdx.x - nb, qkv, ld, o, ldo, dout, lddo, lse, dqkv, ldg, N, H, scale);
 }
 
 // dz[m,n] = dy[m,n] * dropout_scale(m*N+n) * gelu'(pre[m,n])   (act=1)   or   dy * dropout_scale (act=0)
@@ -264,6 +329,17 @@ __global__ void add_rows_f32_kernel(float* __restrict__ dst, long long ldd, cons
   }
 }
 
+// keys staged per pass.  Measured inside the training step (profiles/r1_timeline_*.txt): staging all 729 keys at once
+// (24-30 KB of shared memory per CTA) makes the kernel slower next to the persistent convolution CTAs than 128-key
+// tiles (4-5 KB), although it is faster stand-alone; HDF_ATTN_TILE overrides for experiments.
+int attn_tile(int N) {
+  static const int cfg = getenv("HDF_ATTN_TILE") ? atoi(getenv("HDF_ATTN_TILE")) : AT;
+  int t = (N + AT - 1) / AT * AT;
+  if (t > cfg) t = cfg;
+  t = t / AT * AT;
+  return t < AT ? AT : (t > 1024 ? 1024 : t);
+}
+
 int ln_blocks(int M) {
   int b = cdiv(M, 8);
   return b > 296 ? 296 : (b < 1 ? 1 : b);
@@ -302,8 +378,9 @@ int hdf_layernorm_bwd(const float* dy, long long ldd, const float* x, long long 
 int hdf_attention_fwd(const float* qkv, long long ld, float* o, long long ldo, float* lse, int B, int N, int H, float scale,
                       void* stream) {
   HDF_REQUIRE(qkv && o && lse && (ld % 4 == 0) && (ldo % 4 == 0), "hdf_attention_fwd: bad args");
-  dim3 grid(cdiv(N, AT), H, B);
-  attn_fwd_kernel<<<grid, AT, 0, (cudaStream_t)stream>>>(qkv, ld, o, ldo, lse, N, H, scale);
+  dim3 grid(cdiv(N, AQ), H, B);
+  const int T = attn_tile(N);
+  attn_fwd_kernel<<<grid, AT, (size_t)T * 32, (cudaStream_t)stream>>>(qkv, ld, o, ldo, lse, N, H, scale, T);
   HDF_LAUNCH_CHECK("hdf_attention_fwd");
   return HDF_OK;
 }
@@ -312,11 +389,10 @@ int hdf_attention_bwd(const float* qkv, long long ld, const float* o, long long 
                       const float* lse, float* dqkv, long long ldg, int B, int N, int H, float scale, void* stream) {
   HDF_REQUIRE(qkv && o && dout && lse && dqkv && (ld % 4 == 0) && (ldo % 4 == 0) && (lddo % 4 == 0) && (ldg % 4 == 0),
               "hdf_attention_bwd: bad args");
-  dim3 grid(cdiv(N, AT), H, B);
-  attn_bwd_dq_kernel<<<grid, AT, 0, (cudaStream_t)stream>>>(qkv, ld, o, ldo, dout, lddo, lse, dqkv, ldg, N, H, scale);
-  HDF_LAUNCH_CHECK("hdf_attention_bwd/dq");
-  attn_bwd_dkv_kernel<<<grid, AT, 0, (cudaStream_t)stream>>>(qkv, ld, o, ldo, dout, lddo, lse, dqkv, ldg, N, H, scale);
-  HDF_LAUNCH_CHECK("hdf_attention_bwd/dkv");
+  dim3 grid(2 * cdiv(N, AQ), H, B);
+  const int T = attn_tile(N);
+  attn_bwd_kernel<<<grid, AT, (size_t)T * 40, (cudaStream_t)stream>>>(qkv, ld, o, ldo, dout, lddo, lse, dqkv, ldg, N, H, scale, T);
+  HDF_LAUNCH_CHECK("hdf_attention_bwd");
   return HDF_OK;
 }
 
@@ -410,20 +486,24 @@ __global__ void __launch_bounds__(128) dct_c_fwd_kernel(const DctCParams q) {
   float* W2T = W1T + FG * FH;       // [64][32]
   float* xs = W2T + FH * FG;        // [32 rows][64]
   const int tid = threadIdx.x;
-  for (int i = tid; i < FG * FG; i += 128) WoT[(i % FG) * FG + i / FG] = q.Wo[i];
-  for (int i = tid; i < FH * FG; i += 128) W1T[(i % FG) * FH + i / FG] = q.W1[i];   // W1 [64][32]
-  for (int i = tid; i < FG * FH; i += 128) W2T[(i % FH) * FG + i / FH] = q.W2[i];   // W2 [32][64]
-  __syncthreads();
   const int rl = tid / 4, sub = tid % 4;
   const long long row = (long long)blockIdx.x * FR + rl;
   const bool ok = row < q.R;
   const long long rr = ok ? row : 0;
+  // every global input of the thread is requested up front, together with the weights: one round trip to memory
+  // instead of three dependent ones (this kernel sits on the forward critical path next to the convolution kernels)
+  float p_o[8], p_h0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { p_o[j] = q.o[rr * FG + sub * 8 + j]; p_h0[j] = q.h0[rr * FG + sub * 8 + j]; }
   const unsigned long long seed = q.seed + (q.seed_ptr ? *q.seed_ptr : 0ull);
+  for (int i = tid; i < FG * FG; i += 128) WoT[(i % FG) * FG + i / FG] = q.Wo[i];
+  for (int i = tid; i < FH * FG; i += 128) W1T[(i % FG) * FH + i / FG] = q.W1[i];   // W1 [64][32]
+  for (int i = tid; i < FG * FH; i += 128) W2T[(i % FH) * FG + i / FH] = q.W2[i];   // W2 [32][64]
   float* xr = xs + rl * FH;
   // ---- h1 = drop_a(o Wo^T + bo) + h0
 #pragma unroll
-  for (int j = 0; j < 8; ++j) xr[sub * 8 + j] = q.o[rr * FG + sub * 8 + j];
-  __syncwarp();
+  for (int j = 0; j < 8; ++j) xr[sub * 8 + j] = p_o[j];
+  __syncthreads();
   float h1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) h1[j] = q.bo[sub * 8 + j];
@@ -431,7 +511,7 @@ __global__ void __launch_bounds__(128) dct_c_fwd_kernel(const DctCParams q) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = sub * 8 + j;
-    h1[j] = h1[j] * hdf_dropout_scale(seed, q.ida, (unsigned long long)rr * FG + c, q.p) + q.h0[rr * FG + c];
+    h1[j] = h1[j] * hdf_dropout_scale(seed, q.ida, (unsigned long long)rr * FG + c, q.p) + p_h0[j];
   }
   float hcur[8];
 #pragma unroll
@@ -536,6 +616,18 @@ __global__ void __launch_bounds__(128) dct_c_bwd_kernel(const DctCBwdParams q) {
   const long long rr = ok ? row : 0;
   const float live = ok ? 1.f : 0.f;
   const unsigned long long seed = q.seed + (q.seed_ptr ? *q.seed_ptr : 0ull);
+  // per-row inputs of both passes, requested before anything is consumed (one round trip instead of six)
+  float p_dg2[8], p_zb[16], p_z[16], p_h2[8], p_h1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = sub * 8 + j;
+    p_dg2[j] = q.dg2[rr * q.ldg + c];
+    p_h2[j] = q.h2[rr * FG + c];
+    p_h1[j] = q.h1[rr * FG + c];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { p_zb[j] = q.z1b[rr * FH + sub * 16 + j]; p_z[j] = q.z1[rr * FH + sub * 16 + j]; }
+  const float p_m3 = q.m3[rr], p_m2 = q.m2[rr], p_r3 = q.r3[rr], p_r2 = q.r2[rr];
   // stage the saved activations needed by the weight gradients
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -559,25 +651,25 @@ __global__ void __launch_bounds__(128) dct_c_bwd_kernel(const DctCBwdParams q) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = sub * 8 + j;
-    dzz[j] = live * q.dg2[rr * q.ldg + c] * hdf_dropout_scale(seed, q.ide, (unsigned long long)rr * FG + c, q.p);
+    dzz[j] = live * p_dg2[j] * hdf_dropout_scale(seed, q.ide, (unsigned long long)rr * FG + c, q.p);
     s_dzz[rl * FG + c] = dzz[j];
     xr[c] = dzz[j];
   }
   __syncwarp();
+#pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
     // d(hidden) = dzz W2 ; dz = d(hidden) * mask * gelu'(z)
     float dhid[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) dhid[j] = 0.f;
     rowmm<FG, FH>(xr, W2, sub, dhid);
-    const float* zsv = pass == 0 ? q.z1b : q.z1;
     const unsigned idh = pass == 0 ? q.idd : q.idb;
     float* s_dz = pass == 0 ? s_dz1b : s_dz1;
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int c = sub * 16 + j;
-      const float dz = dhid[j] * hdf_dropout_scale(seed, idh, (unsigned long long)rr * FH + c, q.p) * gelu_grad(zsv[rr * FH + c]);
+      const float dz = dhid[j] * hdf_dropout_scale(seed, idh, (unsigned long long)rr * FH + c, q.p) * gelu_grad(pass == 0 ? p_zb[j] : p_z[j]);
       s_dz[rl * FH + c] = live * dz;
       xr[c] = dz;
     }
@@ -587,13 +679,12 @@ __global__ void __launch_bounds__(128) dct_c_bwd_kernel(const DctCBwdParams q) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) dn[j] = 0.f;
     rowmm<FH, FG>(xr, W1, sub, dn);
-    const float* hsv = pass == 0 ? q.h2 : q.h1;
-    const float mu = (pass == 0 ? q.m3 : q.m2)[rr], rs = (pass == 0 ? q.r3 : q.r2)[rr];
+    const float mu = pass == 0 ? p_m3 : p_m2, rs = pass == 0 ? p_r3 : p_r2;
     float xh[8], a = 0.f, b = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = sub * 8 + j;
-      xh[j] = (hsv[rr * FG + c] - mu) * rs;
+      xh[j] = ((pass == 0 ? p_h2[j] : p_h1[j]) - mu) * rs;
       const float g = dn[j] * q.gm[c];
       a += g;
       b += g * xh[j];

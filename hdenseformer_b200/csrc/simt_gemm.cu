@@ -34,41 +34,56 @@ __global__ void __launch_bounds__(NT) gemm_tile_kernel(AL al, BL bl, EP ep, int 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
-    float av[4], bv[4];
-    if (AL::M_CONTIG) {
-      const int k = tid / 16, m = (tid % 16) * 4;
-      al.load4(m0 + m, k0 + k, kend, av);
-      *reinterpret_cast<float4*>(&As[k][m]) = make_float4(av[0], av[1], av[2], av[3]);
-    } else {
-      const int m = tid / 4, k = (tid % 4) * 4;
-      al.load4(m0 + m, k0 + k, kend, av);
+  // Register prefetch, PF K-chunks deep: the token GEMMs (M ~ 1.5 k rows, K <= 224) run as a handful of CTAs next to the
+  // persistent convolution kernels, where every dependent global round trip costs microseconds; with the loads of the
+  // next PF chunks in flight a K = 224 product needs ~4 round trips instead of 14.
+  constexpr int PF = 4;
+  float av[PF][4], bv[PF][4];
+  const int nchunks = (kend - kbeg + BK - 1) / BK;
+  auto load_ab = [&](int k0, float* a4, float* b4) {
+    if (AL::M_CONTIG) al.load4(m0 + (tid % 16) * 4, k0 + tid / 16, kend, a4);
+    else al.load4(m0 + tid / 4, k0 + (tid % 4) * 4, kend, a4);
+    if (BL::N_CONTIG) bl.load4(k0 + tid / 16, n0 + (tid % 16) * 4, kend, b4);
+    else bl.load4(k0 + (tid % 4) * 4, n0 + tid / 4, kend, b4);
+  };
 #pragma unroll
-      for (int i = 0; i < 4; ++i) As[k + i][m] = av[i];
+  for (int p = 0; p < PF; ++p)
+    if (p < nchunks) load_ab(kbeg + p * BK, av[p], bv[p]);
+  for (int c0 = 0; c0 < nchunks; c0 += PF) {
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+      const int c = c0 + p;
+      if (c < nchunks) {      // block-uniform
+        if (AL::M_CONTIG) {
+          *reinterpret_cast<float4*>(&As[tid / 16][(tid % 16) * 4]) = make_float4(av[p][0], av[p][1], av[p][2], av[p][3]);
+        } else {
+          const int m = tid / 4, k = (tid % 4) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) As[k + i][m] = av[p][i];
+        }
+        if (BL::N_CONTIG) {
+          *reinterpret_cast<float4*>(&Bs[tid / 16][(tid % 16) * 4]) = make_float4(bv[p][0], bv[p][1], bv[p][2], bv[p][3]);
+        } else {
+          const int n = tid / 4, k = (tid % 4) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) Bs[k + i][n] = bv[p][i];
+        }
+        __syncthreads();
+        if (c + PF < nchunks) load_ab(kbeg + (c + PF) * BK, av[p], bv[p]);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+          const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+          const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+          const float aa[4] = {a.x, a.y, a.z, a.w};
+          const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
     }
-    if (BL::N_CONTIG) {
-      const int k = tid / 16, n = (tid % 16) * 4;
-      bl.load4(k0 + k, n0 + n, kend, bv);
-      *reinterpret_cast<float4*>(&Bs[k][n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-    } else {
-      const int n = tid / 4, k = (tid % 4) * 4;
-      bl.load4(k0 + k, n0 + n, kend, bv);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) Bs[k + i][n] = bv[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float aa[4] = {a.x, a.y, a.z, a.w};
-      const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
-    }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -1137,7 +1137,9 @@ static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void
   const int ntaps_total = p.taps.first[p.taps.ncls];
   const size_t bres_bytes = (size_t)ntaps_total * p.kchunks * p.b_region;
   static const char* no_res = getenv("HDF_TC_NO_RESIDENT");
-  p.b_resident = (bres_bytes <= 114 * 1024 && !no_res) ? 1 : 0;
+  static const int smem_kb_cfg = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
+  // with a reduced budget (experiments) resident weights must leave room for >= 4 ring stages of the largest input box
+  p.b_resident = (bres_bytes <= 114 * 1024 && (smem_kb_cfg >= 200 || bres_bytes + 4 * 24 * 1024 <= (size_t)smem_kb_cfg * 1024) && !no_res) ? 1 : 0;
   p.khfold = 0;
   p.line_bytes = (uint32_t)p.TW * p.KC * 2u;
   static const char* no_kh = getenv("HDF_TC_NO_KHFOLD");

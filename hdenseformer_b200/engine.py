@@ -100,7 +100,9 @@ class Engine:
     def _side_stream(self, dev, idx=0):
         key = (dev.index if dev.index is not None else torch.cuda.current_device(), idx)
         if key not in self._side:
-            self._side[key] = torch.cuda.Stream(device=dev)
+            # HDF_SIDE_PRIORITY=1: the token-chain streams outrank the main stream's fat kernels in the block scheduler
+            prio = -1 if os.environ.get("HDF_SIDE_PRIORITY") == "1" else 0
+            self._side[key] = torch.cuda.Stream(device=dev, priority=prio)
         return self._side[key]
 
     # ------------------------------------------------------------------ conv helpers

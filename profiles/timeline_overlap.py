@@ -72,7 +72,7 @@ print("upsample2_fwd ends", [round((k[1] - t0) / 1e3, 3) for k in ks if "upsampl
 print("maxpool_fwd starts", [round((k[0] - t0) / 1e3, 3) for k in ks if "maxpool_fwd" in k[2]])
 print("first 3 tc_conv_fwd (start,end)", [(round((k[0] - t0) / 1e3, 3), round((k[1] - t0) / 1e3, 3)) for k in ks if "tc_conv_fwd" in k[2]][:8])
 print("loss_reduce first start", first("loss_reduce"))
-print("attn_bwd_dq first/last", first("attn_bwd_dq"), last("attn_bwd_dq"))
+print("attn_bwd first/last", first("attn_bwd"), last("attn_bwd"))
 print("last tc_conv_wgrad end", last("tc_conv_wgrad"))
 print("adam start", first("FusedOptimizer"))
 # per-kernel average in-step duration for the token kernels
@@ -82,3 +82,23 @@ for s, e, n, _ in ks:
     agg[key][0] += 1; agg[key][1] += (e - s) / 1e3
 for k, (n, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
     print(f"{tt:8.2f} ms {n:5d} {1e3*tt/n:8.1f} us  {k}")
+
+# ---- the token-kernel chain of the forward pass: (start ms, duration us, gap to the previous kernel of the same stream us, name)
+import re
+def short(n):
+    m = re.search(r"(\w+)(<|\()", n.replace("(anonymous namespace)::", "").replace("void ", ""))
+    return m.group(1) if m else n[:30]
+evs = [(e.time_range.start, e.time_range.end, short(e.name), getattr(e, "stream", None)) for e in ev]
+streams = collections.defaultdict(list)
+for s, e, n, st in sorted(evs):
+    streams[st].append((s, e, n))
+print("streams:", {k: len(v) for k, v in streams.items()})
+for st, lst in streams.items():
+    toks = [x for x in lst if any(t in x[2] for t in ("attn", "dct_", "gemm_tile", "layernorm", "reduce_partials", "patch"))]
+    if len(toks) < 50: continue
+    print(f"--- stream {st}: first 40 kernels of the token chain")
+    prev = None
+    for s, e, n in lst[:40]:
+        print(f"  {(s - t0) / 1e3:8.3f} ms  {(e - s):7.1f} us  gap {(s - prev) if prev else 0:7.1f} us  {n}")
+        prev = e
+    break
