@@ -1137,9 +1137,15 @@ static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void
   const int ntaps_total = p.taps.first[p.taps.ncls];
   const size_t bres_bytes = (size_t)ntaps_total * p.kchunks * p.b_region;
   static const char* no_res = getenv("HDF_TC_NO_RESIDENT");
-  static const int smem_kb_cfg = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
+  // two resident CTAs per SM (each <= 110 KB of shared memory and <= 256 TMEM columns) when the folded weights are small
+  // enough to stay resident beside >= 3 ring stages: two MMA-issue streams per SM hide each other's barrier round trips
+  static const int fwd_ctas_cfg = getenv("HDF_TC_FWD_CTAS") ? atoi(getenv("HDF_TC_FWD_CTAS")) : 1;
+  const size_t kh_stage = ((size_t)p.TW * (128 / p.TW + 2) * p.KC * 2u + 1023u) & ~(size_t)1023u;
+  const bool two_ctas = fwd_ctas_cfg >= 2 && p.fold && 2 * p.Nmma <= 256 && bres_bytes + 3 * kh_stage <= 108 * 1024 && !no_res;
+  static const int smem_kb_env = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
+  const int smem_kb_cfg = two_ctas ? 108 : smem_kb_env;
   // with a reduced budget (experiments) resident weights must leave room for >= 4 ring stages of the largest input box
-  p.b_resident = (bres_bytes <= 114 * 1024 && (smem_kb_cfg >= 200 || bres_bytes + 4 * 24 * 1024 <= (size_t)smem_kb_cfg * 1024) && !no_res) ? 1 : 0;
+  p.b_resident = two_ctas ? 1 : (bres_bytes <= 114 * 1024 && (smem_kb_cfg >= 200 || bres_bytes + 4 * 24 * 1024 <= (size_t)smem_kb_cfg * 1024) && !no_res) ? 1 : 0;
   p.khfold = 0;
   p.line_bytes = (uint32_t)p.TW * p.KC * 2u;
   static const char* no_kh = getenv("HDF_TC_NO_KHFOLD");
@@ -1159,7 +1165,7 @@ static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void
   p.stage_bytes = a_region_h + (p.b_resident ? 0u : p.b_region);
   // total dynamic smem target per CTA (KB): smaller values leave room for the transformer branch's small kernels to
   // co-reside with the persistent conv CTAs on the same SM
-  static const int smem_kb = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
+  const int smem_kb = smem_kb_cfg;
   const size_t ring_budget = (size_t)smem_kb * 1024 - (p.b_resident ? bres_bytes : 0);
   p.stages = (int)(ring_budget / p.stage_bytes);
   if (p.stages > 12) p.stages = 12;
@@ -1215,7 +1221,8 @@ static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void
     if (e != cudaSuccess) { hdf_set_error("hdf_tc_conv3d_fwd: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
     configured = 227 * 1024;
   }
-  const int grid = p.num_tiles < hdf_sm_count_cached() ? p.num_tiles : hdf_sm_count_cached();
+  const int max_ctas = (two_ctas ? 2 : 1) * hdf_sm_count_cached();
+  const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
   tc_conv_fwd_kernel<<<grid, FWD_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_fwd");
   if (p.dbg) {   // debug only: synchronous dump of CTA 0's wait-cycle counters
@@ -1242,11 +1249,24 @@ int hdf_tc_wgrad_supported(int mode, int Cin, int Cout) {
   return wgrad_ok(Cin) && wgrad_ok(Cout) && (mode == 0 ? Cout : Cin) <= 256;
 }
 
+// Resident CTAs per SM the plan aims for.  Measured (profiles/r1_microbench_conv_v6_wgrad_2cta.txt): one CTA has a single
+// TMA-issuing and a single MMA-issuing thread whose dependent waits serialise; two CTAs per SM (<= 112 KB of shared
+// memory and <= 256 TMEM columns each) overlap them and make the narrow layers (Cin 16/32: 1.71 -> 0.96 ms at 144^3)
+// much faster, at the price of more passes over the (27x smaller) fixed operand.
+static int wgrad_target_ctas(int Cin, int Cout) {
+  static const int cfg = getenv("HDF_TC_WGRAD_CTAS") ? atoi(getenv("HDF_TC_WGRAD_CTAS")) : 0;
+  if (cfg > 0) return cfg;
+  (void)Cin; (void)Cout;
+  return 2;
+}
+
 static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradParams& p, int ntaps = 27) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.ntaps = ntaps;
   p.a_scale = 1;
+  static const int kv_cfg = getenv("HDF_TC_WGRAD_KV") ? atoi(getenv("HDF_TC_WGRAD_KV")) : 0;
   p.KV = (Cout > 128) ? 64 : 128;
+  if (kv_cfg == 64 || kv_cfg == 128) p.KV = (Cout > 128) ? 64 : kv_cfg;
   // tile = KV voxels
   {
     long long best = -1; p.TD = p.TH = p.TW = 1;
@@ -1264,8 +1284,6 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   p.sub_per_tap = Cin / p.CW;
   p.total_sub = ntaps * p.sub_per_tap;
   p.total_groups = cdiv(p.total_sub, p.SPG);
-  p.groups_per_pass = 512 / Cout;
-  if (p.groups_per_pass > p.total_groups) p.groups_per_pass = p.total_groups;
   p.CWn = Cout < 64 ? Cout : 64;
   p.nsub_b = Cout / p.CWn;
   p.a_sub_bytes = (uint32_t)p.KV * p.CW * 2;
@@ -1273,9 +1291,22 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   p.b_sub_bytes = (uint32_t)p.KV * p.CWn * 2;
   p.b_stage_bytes = (p.b_sub_bytes * p.nsub_b + 1023u) & ~1023u;
   static const int smem_kb = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
-  p.a_stages = (int)(((unsigned)smem_kb * 1024u - 2u * p.b_stage_bytes) / p.a_stage_bytes);
-  if (p.a_stages > 6) p.a_stages = 6;
+  static const int max_stages = getenv("HDF_TC_WGRAD_STAGES") ? atoi(getenv("HDF_TC_WGRAD_STAGES")) : 6;
+  int ctas = wgrad_target_ctas(Cin, Cout);
+  for (;; --ctas) {
+    // per-CTA budgets for `ctas` resident CTAs per SM (227 KB and 512 TMEM columns per SM; ~1.5 KB of barriers/slack each)
+    const unsigned budget = ctas <= 1 ? (unsigned)smem_kb * 1024u : (unsigned)(224 * 1024 / ctas) - 2048u;
+    int tcols = 512;
+    for (int c = 1; c < ctas; c *= 2) tcols /= 2;                 // 512, 256, 128, 128 ...
+    p.groups_per_pass = tcols / Cout;
+    if (p.groups_per_pass > p.total_groups) p.groups_per_pass = p.total_groups;
+    const long long room = (long long)budget - 2ll * p.b_stage_bytes;
+    p.a_stages = room > 0 ? (int)(room / p.a_stage_bytes) : 0;
+    if (p.a_stages > max_stages) p.a_stages = max_stages;
+    if (ctas <= 1 || (p.a_stages >= 2 && p.groups_per_pass >= 1)) break;
+  }
   if (p.a_stages < 2) p.a_stages = 2;
+  if (p.groups_per_pass < 1) p.groups_per_pass = 1;
   const int ia = p.CW * 2, ib = p.CWn * 2;
   p.a_layout = ia == 128 ? 2u : ia == 64 ? 4u : 6u;
   p.b_layout = ib == 128 ? 2u : ib == 64 ? 4u : 6u;
@@ -1285,7 +1316,7 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   while (cols < (uint32_t)(p.groups_per_pass * Cout)) cols *= 2;
   p.tmem_cols = cols;
   const int passes = cdiv(p.total_groups, p.groups_per_pass);
-  // split-K: ~2 CTAs per SM in total, at least 8 chunks per slab
+  // split-K: ~2 CTAs per SM in total (one wave when two are resident), at least 8 chunks per slab
   int slabs = cdiv(2 * hdf_sm_count_cached(), passes);
   const int max_slabs = p.num_chunks / 8 > 0 ? p.num_chunks / 8 : 1;
   if (slabs > max_slabs) slabs = max_slabs;

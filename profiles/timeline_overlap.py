@@ -102,3 +102,19 @@ for st, lst in streams.items():
         print(f"  {(s - t0) / 1e3:8.3f} ms  {(e - s):7.1f} us  gap {(s - prev) if prev else 0:7.1f} us  {n}")
         prev = e
     break
+
+# ---- a window of the backward pass (all streams): what runs next to the transformer-backward chain
+lo, hi = float(os.environ.get("HDF_TL_LO", 24.0)), float(os.environ.get("HDF_TL_HI", 24.9))
+print(f"--- kernels starting in [{lo}, {hi}] ms")
+for s, e, n, _ in sorted(evs):
+    if lo <= (s - t0) / 1e3 <= hi:
+        print(f"  {(s - t0) / 1e3:8.3f} ms  {(e - s):7.1f} us  {n}")
+
+# ---- token-branch kernels that "took" more than 100 us (waiting for SM resources next to a persistent convolution kernel)
+tok = ("attn", "dct_", "gemm_tile", "layernorm", "reduce_partials", "patch", "ln_param", "act_dropout", "colsum", "posemb")
+slow = [(s, e, n) for s, e, n, _ in sorted(evs) if any(t in n for t in tok) and e - s > 100]
+print(f"--- token kernels longer than 100 us: {len(slow)}, total {sum(e - s for s, e, _ in slow) / 1e3:.2f} ms")
+for s, e, n in slow:
+    co = [(bs, be, bn) for bs, be, bn, _ in evs if "tc_conv" in bn and bs < e and be > s]
+    print(f"  {(s - t0) / 1e3:8.3f} ms  {(e - s):7.1f} us  {n:24s} overlapping: " +
+          ", ".join(f"{bn}[{(bs - t0) / 1e3:.2f}-{(be - t0) / 1e3:.2f}]" for bs, be, bn in co))
