@@ -95,7 +95,18 @@ class _HDFFunction(torch.autograd.Function):
         arena.zero_()
         m._engine.backward(ctx.P, arena.views, ctx.saved, list(gouts), on_grads_ready=m._on_grads_ready)
         ctx.saved = None
-        return (None, None, None, None, None, None, *[arena.views[k] for k in m._keys])
+        # Hand the gradients over as views of the arena instead of returning them to autograd: AccumulateGrad would clone
+        # every view into its own storage (406 device-to-device copies of ~1.5 us each, serial, at the tail of every step:
+        # profiles/r1_timeline_v17.txt).  Accumulation into a foreign .grad tensor is still honoured.
+        for k, prm in ctx.P.items():
+            if not prm.requires_grad:
+                continue
+            v = arena.views[k]
+            if prm.grad is None:
+                prm.grad = v
+            elif prm.grad.data_ptr() != v.data_ptr():
+                prm.grad.add_(v)
+        return (None,) * (6 + len(m._keys))
 
 
 class HDenseFormer(nn.Module):

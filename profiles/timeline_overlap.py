@@ -104,11 +104,12 @@ for st, lst in streams.items():
     break
 
 # ---- a window of the backward pass (all streams): what runs next to the transformer-backward chain
-lo, hi = float(os.environ.get("HDF_TL_LO", 24.0)), float(os.environ.get("HDF_TL_HI", 24.9))
-print(f"--- kernels starting in [{lo}, {hi}] ms")
-for s, e, n, _ in sorted(evs):
-    if lo <= (s - t0) / 1e3 <= hi:
-        print(f"  {(s - t0) / 1e3:8.3f} ms  {(e - s):7.1f} us  {n}")
+for win in os.environ.get("HDF_TL_WINDOWS", "24.0:24.9").split(","):
+    lo, hi = (float(v) for v in win.split(":"))
+    print(f"--- kernels starting in [{lo}, {hi}] ms")
+    for s, e, n, _ in sorted(evs):
+        if lo <= (s - t0) / 1e3 <= hi:
+            print(f"  {(s - t0) / 1e3:8.3f} ms  {(e - s):7.1f} us  {n}")
 
 # ---- token-branch kernels that "took" more than 100 us (waiting for SM resources next to a persistent convolution kernel)
 tok = ("attn", "dct_", "gemm_tile", "layernorm", "reduce_partials", "patch", "ln_param", "act_dropout", "colsum", "posemb")
