@@ -170,6 +170,11 @@ struct TcConvParams {
   bf16* y;
 };
 
+// Dynamic shared memory budget of one persistent convolution CTA.  192 KB (not the full 227) leaves ~34 KB of the SM for
+// the token-branch kernels of the side streams (dct_c_fwd needs 28.7 KB), which otherwise wait for the CTA to drain.
+#ifndef HDF_TC_SMEM_KB_DEFAULT
+#define HDF_TC_SMEM_KB_DEFAULT 192
+#endif
 constexpr int TC_THREADS = 256;     // wgrad kernel: warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 epilogue
 constexpr int FWD_THREADS = 288;    // fwd kernel: warps 0-3 producers, 4 MMA + TMEM alloc, 5-8 epilogue
 constexpr int CP_LAG = 3;           // cp.async groups kept in flight per producer thread
@@ -1142,10 +1147,10 @@ static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void
   static const int fwd_ctas_cfg = getenv("HDF_TC_FWD_CTAS") ? atoi(getenv("HDF_TC_FWD_CTAS")) : 1;
   const size_t kh_stage = ((size_t)p.TW * (128 / p.TW + 2) * p.KC * 2u + 1023u) & ~(size_t)1023u;
   const bool two_ctas = fwd_ctas_cfg >= 2 && p.fold && 2 * p.Nmma <= 256 && bres_bytes + 3 * kh_stage <= 108 * 1024 && !no_res;
-  static const int smem_kb_env = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
+  static const int smem_kb_env = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : HDF_TC_SMEM_KB_DEFAULT;
   const int smem_kb_cfg = two_ctas ? 108 : smem_kb_env;
   // with a reduced budget (experiments) resident weights must leave room for >= 4 ring stages of the largest input box
-  p.b_resident = two_ctas ? 1 : (bres_bytes <= 114 * 1024 && (smem_kb_cfg >= 200 || bres_bytes + 4 * 24 * 1024 <= (size_t)smem_kb_cfg * 1024) && !no_res) ? 1 : 0;
+  p.b_resident = two_ctas ? 1 : (bres_bytes <= 114 * 1024 && (smem_kb_cfg >= HDF_TC_SMEM_KB_DEFAULT || bres_bytes + 4 * 24 * 1024 <= (size_t)smem_kb_cfg * 1024) && !no_res) ? 1 : 0;
   p.khfold = 0;
   p.line_bytes = (uint32_t)p.TW * p.KC * 2u;
   static const char* no_kh = getenv("HDF_TC_NO_KHFOLD");
@@ -1218,6 +1223,10 @@ static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    // full 228 KB carve-out even when the CTA asks for less: the driver otherwise picks the smallest configuration that
+    // fits THIS kernel (e.g. 196 KB for a 194 KB CTA), and the side streams' kernels find no shared memory left on the SM
+    if (e == cudaSuccess && getenv("HDF_NO_MAX_CARVEOUT") == nullptr)
+      e = cudaFuncSetAttribute(tc_conv_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { hdf_set_error("hdf_tc_conv3d_fwd: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
     configured = 227 * 1024;
   }
@@ -1290,12 +1299,13 @@ static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradP
   p.a_stage_bytes = p.a_sub_bytes * p.SPG;          // = KV*256 bytes, multiple of 1024
   p.b_sub_bytes = (uint32_t)p.KV * p.CWn * 2;
   p.b_stage_bytes = (p.b_sub_bytes * p.nsub_b + 1023u) & ~1023u;
-  static const int smem_kb = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : 200;
+  static const int smem_kb = getenv("HDF_TC_SMEM_KB") ? atoi(getenv("HDF_TC_SMEM_KB")) : HDF_TC_SMEM_KB_DEFAULT;
   static const int max_stages = getenv("HDF_TC_WGRAD_STAGES") ? atoi(getenv("HDF_TC_WGRAD_STAGES")) : 6;
   int ctas = wgrad_target_ctas(Cin, Cout);
   for (;; --ctas) {
     // per-CTA budgets for `ctas` resident CTAs per SM (227 KB and 512 TMEM columns per SM; ~1.5 KB of barriers/slack each)
-    const unsigned budget = ctas <= 1 ? (unsigned)smem_kb * 1024u : (unsigned)(224 * 1024 / ctas) - 2048u;
+    static const int pair_kb = getenv("HDF_TC_WGRAD_PAIR_KB") ? atoi(getenv("HDF_TC_WGRAD_PAIR_KB")) : 224;
+    const unsigned budget = ctas <= 1 ? (unsigned)smem_kb * 1024u : (unsigned)(pair_kb * 1024 / ctas) - 2048u;
     int tcols = 512;
     for (int c = 1; c < ctas; c *= 2) tcols /= 2;                 // 512, 256, 128, 128 ...
     p.groups_per_pass = tcols / Cout;
@@ -1428,6 +1438,10 @@ static int tc_wgrad2_launch(int mode, const void* x, long long ldx, const void* 
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    // full 228 KB carve-out even when the CTA asks for less: the driver otherwise picks the smallest configuration that
+    // fits THIS kernel (e.g. 196 KB for a 194 KB CTA), and the side streams' kernels find no shared memory left on the SM
+    if (e == cudaSuccess && getenv("HDF_NO_MAX_CARVEOUT") == nullptr)
+      e = cudaFuncSetAttribute(tc_conv_wgrad2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { hdf_set_error("hdf_tc_conv3d_wgrad: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
     configured = true;
   }
@@ -1518,6 +1532,10 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    // full 228 KB carve-out even when the CTA asks for less: the driver otherwise picks the smallest configuration that
+    // fits THIS kernel (e.g. 196 KB for a 194 KB CTA), and the side streams' kernels find no shared memory left on the SM
+    if (e == cudaSuccess && getenv("HDF_NO_MAX_CARVEOUT") == nullptr)
+      e = cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { hdf_set_error("hdf_tc_conv3d_wgrad: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
     configured = true;
   }
@@ -1613,6 +1631,8 @@ int hdf_stem_conv_wgrad(const void* xcol_bf16, const void* dy, long long ldy, fl
   }
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + 2 * (size_t)p.b_stage_bytes + 1024 + 8 * (2 * p.a_stages + 6) + 16;
   cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e == cudaSuccess && getenv("HDF_NO_MAX_CARVEOUT") == nullptr)
+    e = cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) { hdf_set_error("hdf_stem_conv_wgrad: smem attribute: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
   HDF_REQUIRE(smem <= 227 * 1024, "hdf_stem_conv_wgrad: smem plan too large (%zu)", smem);
   dim3 grid(p.num_slabs, passes);

@@ -87,6 +87,10 @@ class Engine:
         # tensor-core work is available to overlap the branch's long chain of small, latency-bound kernels.
         self.defer_wgrad = os.environ.get("HDF_NO_DEFER_WGRAD") is None
         self._deferred = []
+        # stream priorities (lower = more urgent; the graphed trainer captures the main path at -1)
+        self.fwd_side_priority = int(os.environ.get("HDF_FWD_SIDE_PRIO", "-2"))
+        self.bwd_side_priority = int(os.environ.get("HDF_BWD_SIDE_PRIO", "0"))
+        self.patch_first = os.environ.get("HDF_NO_PATCH_FIRST") is None   # encoder starts after the patch-embedding GEMMs
         self.use_stem = os.environ.get("HDF_NO_STEM") is None   # im2col + GEMM first layer (bf16 tensor-core path only)
         self.fused_dct = True     # fused post-attention chain kernels (csrc/dct.cu) instead of ~40 single-op launches
         # fused layer-head kernels (Linear_l + LN1 + to_qkv): measured slower than the three single-op launches on B200
@@ -97,11 +101,13 @@ class Engine:
         self._keep_alive = None
         self._defer_open = False
 
-    def _side_stream(self, dev, idx=0):
-        key = (dev.index if dev.index is not None else torch.cuda.current_device(), idx)
+    def _side_stream(self, dev, idx=0, phase="f"):
+        """Side streams of the transformer branch.  Forward and backward use different stream objects because they want
+        different priorities: in the forward pass the token chain is the critical path (the main stream idles at the
+        at3 join), in the backward pass it has slack and must not steal SM time from the convolution kernels."""
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), idx, phase)
         if key not in self._side:
-            # HDF_SIDE_PRIORITY=1: the token-chain streams outrank the main stream's fat kernels in the block scheduler
-            prio = -1 if os.environ.get("HDF_SIDE_PRIORITY") == "1" else 0
+            prio = self.fwd_side_priority if phase == "f" else self.bwd_side_priority
             self._side[key] = torch.cuda.Stream(device=dev, priority=prio)
         return self._side[key]
 
@@ -373,6 +379,7 @@ class Engine:
         c.tr = []
         p = DROP_P if training else 0.0
         mod_streams = []
+        pe_events = []
         for i in range(M):
             pre = f"attns.{i}."
             tr = dict(blocks=[])
@@ -386,6 +393,10 @@ class Engine:
             tr["pe_id"] = ids()
             ops.patch_embed_fwd(x, i, P[pre + "patch_embeddings.weight"], P[pre + "patch_embeddings.bias"],
                                 P[pre + "position_embeddings"], F[:, :E], p, seed, tr["pe_id"])
+            if side is not None and self.patch_first:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                pe_events.append(ev)
             tok = None
             for b in range(cfg.nblocks):
                 bp = f"{pre}blocks.{b}.0."
@@ -433,6 +444,10 @@ class Engine:
             return at3
 
         # ---------------- encoder; skip tensors are written straight into the decoder concat buffers
+        # The token chain is the forward critical path (the main stream idles ~1 ms at join_at3): let the patch-embedding
+        # GEMMs have the GPU to themselves instead of queueing behind the 41 k blocks of the first encoder kernels.
+        for ev in pe_events:
+            main_stream.wait_event(ev)
         if self.use_tc and self.use_stem and dtype == torch.bfloat16 and ops.stem_supported(M, nf):
             xcl = ops.stem_im2col(x)        # first conv = one GEMM over the gathered taps (csrc/tc_conv.cu, stem path)
         else:
@@ -549,7 +564,7 @@ class Engine:
         dds0 = dcat1[..., nf:]
         ops.maxpool2_bwd(c.cat1[..., nf:], dp1, dds0, True)
         main_stream = torch.cuda.current_stream(dev)
-        side = self._side_stream(dev) if self.use_side_stream else None
+        side = self._side_stream(dev, 0, "b") if self.use_side_stream else None
 
         # ---- transformer-feature up path: at3 <- up3 <- at2 <- up2 <- at1 <- up1 <- attnout <- deep_conv <- attnall.
         # It is the head of the longest remaining dependency chain (the transformer backward hangs off it), and its
@@ -593,7 +608,7 @@ class Engine:
         for i in reversed(range(cfg.M)):
             pre = f"attns.{i}."
             tr = c.tr[i]
-            ms = self._side_stream(dev, i) if (side is not None and i > 0) else None
+            ms = self._side_stream(dev, i, "b") if (side is not None and i > 0) else None
             if ms is not None:
                 ms.wait_event(fork_ev)
                 mod_ctx = torch.cuda.stream(ms)
