@@ -161,6 +161,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hdf_bench_nccl_%h_%p.log")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     net = HDenseFormer_32(2, 2, size, a.depth).to(dev).train()
