@@ -187,12 +187,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
+        if finish is not None:
+            finish()
         e1.record()
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -216,13 +218,34 @@ def main():
     stepper = graphed.step if graphed is not None else dp.step
     step_dev = lambda i: stepper(*devb[i % nb])
 
+    # e2e: every step's batch comes from pinned host memory inside the timed region; with the graphed stepper the copy of
+    # step i+1 is issued on a copy stream so that it overlaps step i's kernels.  Every step's loss is read back to the
+    # host: the 4-byte D2H copy is enqueued right behind the step and consumed one step later (the usual way a training
+    # loop logs its loss without draining the GPU queue every step); the last one is drained inside the timed region.
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending = []
+    losses_read = []
+
+    def drain_one():
+        buf, ev = pending.pop(0)
+        ev.synchronize()
+        losses_read.append(float(buf))     # host read of that step's result
+
     def step_e2e(i):
-        # every step's batch comes from pinned host memory inside the timed region; with the graphed stepper the copy of
-        # step i+1 is issued on a copy stream before step i's result is read back, so it overlaps step i's kernels
         loss = stepper(*host[i % nb])
         if graphed is not None:
             graphed.prefetch(*host[(i + 1) % nb])
-        return loss.item()          # D2H read of the step's result
+        buf = loss_host[i % 2]
+        buf.copy_(loss.detach().float(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        pending.append((buf, ev))
+        if len(pending) > 1:
+            drain_one()
+
+    def finish_e2e():
+        while pending:
+            drain_one()
 
     for i in range(warmup):
         step_dev(i)
@@ -238,7 +261,10 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, a.steps)
+    finish_e2e()
+    losses_read.clear()
+    ms_e2e = timed(step_e2e, a.steps, finish_e2e)
+    assert len(losses_read) == a.steps and all(v == v for v in losses_read), "e2e: every step's loss must reach the host"
 
     vols = a.batch * world * a.steps
     value = vols / (ms / 1e3)
@@ -280,7 +306,8 @@ def main():
                        "algorithmic_tflop_per_volume": gf_step / 1e3, "achieved_tflops": gf_step * value / 1e3},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_e2e / a.steps,
-                    "h2d_bytes_per_step": int(sum(x.numel() * 4 + t.numel() * 4 for x, t in host[:1])), "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": int(sum(x.numel() * 4 + t.numel() * 4 for x, t in host[:1])), "d2h_bytes_per_step": 4,
+                    "readback": "every step's loss is copied to pinned host memory and read one step later (last one inside the timed region)"},
             "gpu_launches": int(launches),
             "roofline": roof,
         }

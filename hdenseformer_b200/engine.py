@@ -90,6 +90,8 @@ class Engine:
         # stream priorities (lower = more urgent; the graphed trainer captures the main path at -1)
         self.fwd_side_priority = int(os.environ.get("HDF_FWD_SIDE_PRIO", "-2"))
         self.bwd_side_priority = int(os.environ.get("HDF_BWD_SIDE_PRIO", "0"))
+        self.prepack = os.environ.get("HDF_NO_PREPACK") is None       # conv weights packed up front on a side stream
+        self._packed, self._packed_open = {}, False
         self.patch_first = os.environ.get("HDF_NO_PATCH_FIRST") is None   # encoder starts after the patch-embedding GEMMs
         self.use_stem = os.environ.get("HDF_NO_STEM") is None   # im2col + GEMM first layer (bf16 tensor-core path only)
         self.fused_dct = True     # fused post-attention chain kernels (csrc/dct.cu) instead of ~40 single-op launches
@@ -112,6 +114,44 @@ class Engine:
         return self._side[key]
 
     # ------------------------------------------------------------------ conv helpers
+    def _pack(self, w, Cin, Cout, sci, sco, flip, cin_valid=None):
+        """bf16 [27][Cout][Cin] operand tiles of a conv weight; taken from the per-step cache when `_prepack` filled it."""
+        key = (w.data_ptr(), Cin, Cout, sci, sco, bool(flip), cin_valid)
+        t = self._packed.get(key)
+        if t is None:
+            t = ops.tc_pack(w, Cin, Cout, sci, sco, flip, cin_valid=cin_valid)
+            if self._packed_open:
+                self._packed[key] = t
+        return t
+
+    def _prepack(self, P, dev, main_stream, need_dgrad):
+        """Pack every tensor-core conv weight of the step (forward and input-gradient layouts) on a side stream at the
+        start of the forward pass: ~40 small kernels leave the main stream's dependency chain (each sat right in front
+        of its convolution).  Returns the event the consumers wait on."""
+        st = self._side_stream(dev, 99, "p")
+        st.wait_stream(main_stream)      # also orders the re-use of last step's buffers behind last step's kernels
+        self._packed = {}
+        self._packed_open = True
+        with torch.cuda.stream(st):
+            for k, w in P.items():
+                if w.dim() != 5 or w.shape[2:] != (3, 3, 3):
+                    continue
+                if k.startswith("upconv_"):          # ConvTranspose3d weight [Cin, Cout, 27]
+                    Cin, Cout = w.shape[0], w.shape[1]
+                    if ops.tc_supported(1, Cin, Cout):
+                        self._pack(w, Cin, Cout, Cout * 27, 27, False)
+                    if need_dgrad and ops.tc_supported(2, Cout, Cin):
+                        self._pack(w, Cout, Cin, 27, Cout * 27, False)
+                else:                                 # Conv3d weight [Cout, Cin, 27]
+                    Cout, Cin = w.shape[0], w.shape[1]
+                    if ops.tc_supported(0, Cin, Cout):
+                        self._pack(w, Cin, Cout, 27, Cin * 27, False, cin_valid=Cin)
+                    if need_dgrad and ops.tc_supported(0, Cout, Cin):
+                        self._pack(w, Cout, Cin, Cin * 27, 27, True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        return ev
+
     def _conv_fwd(self, x, w, bias, out, mode=0):
         """x: [N,D,H,W,Cin] view; w: torch-layout weight; out: [N,Do,Ho,Wo,Cout] view."""
         if mode == 0:    # Conv3d weight [Cout, Cin, 27]
@@ -120,13 +160,13 @@ class Engine:
             if Cx != Cin and Cx == ops.stem_kp(Cin):
                 return ops.stem_conv_fwd(x, w, out)
             if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(0, Cx, Cout):
-                return ops.tc_conv3d_fwd(x, ops.tc_pack(w, Cx, Cout, 27, Cin * 27, False, cin_valid=Cin), bias, out)
+                return ops.tc_conv3d_fwd(x, self._pack(w, Cx, Cout, 27, Cin * 27, False, cin_valid=Cin), bias, out)
             assert Cx == Cin
             wp = ops.conv_pack(w, Cin, Cout, 27, Cin * 27, False)
         else:            # ConvTranspose3d weight [Cin, Cout, 27]
             Cin, Cout = w.shape[0], w.shape[1]
             if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(1, Cin, Cout):
-                return ops.tc_conv3d_fwd(x, ops.tc_pack(w, Cin, Cout, Cout * 27, 27, False), bias, out, mode=1)
+                return ops.tc_conv3d_fwd(x, self._pack(w, Cin, Cout, Cout * 27, 27, False), bias, out, mode=1)
             wp = ops.conv_pack(w, Cin, Cout, Cout * 27, 27, False)
         return ops.conv3d_fwd(x, wp, bias, out, mode)
 
@@ -137,13 +177,13 @@ class Engine:
             Cout, Cin = w.shape[0], w.shape[1]
             if self.use_tc and dy.dtype == torch.bfloat16 and ops.tc_supported(0, Cout, Cin):
                 # GEMM K = Cout (channels of dy), GEMM N = Cin: packed[tap][ci][co] = w[co][ci][26-tap]
-                return ops.tc_conv3d_fwd(dy, ops.tc_pack(w, Cout, Cin, Cin * 27, 27, True), None, out)
+                return ops.tc_conv3d_fwd(dy, self._pack(w, Cout, Cin, Cin * 27, 27, True), None, out)
             wp = ops.conv_pack(w, Cout, Cin, Cin * 27, 27, True)      # packed[tap][co][ci] = w[co][ci][26-tap]
             return ops.conv3d_fwd(dy, wp, None, out, 0)
         Cin, Cout = w.shape[0], w.shape[1]
         if self.use_tc and dy.dtype == torch.bfloat16 and ops.tc_supported(2, Cout, Cin):
             # strided conv over dy: GEMM K = Cout, N = Cin; packed[tap][n=ci][k=co] = w[ci][co][tap]
-            return ops.tc_conv3d_fwd(dy, ops.tc_pack(w, Cout, Cin, 27, Cout * 27, False), None, out, mode=2)
+            return ops.tc_conv3d_fwd(dy, self._pack(w, Cout, Cin, 27, Cout * 27, False), None, out, mode=2)
         wp = ops.conv_pack(w, Cout, Cin, 27, Cout * 27, False)         # packed[tap][co][ci] = w[ci][co][tap]
         return ops.conv3d_fwd(dy, wp, None, out, 2)
 
@@ -362,6 +402,10 @@ class Engine:
 
         main_stream = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.use_side_stream else None
+        pack_ev = None
+        self._packed, self._packed_open = {}, False
+        if side is not None and self.prepack and self.use_tc and dtype == torch.bfloat16:
+            pack_ev = self._prepack(P, dev, main_stream, need_dgrad=save)
         if side is not None:
             side.wait_stream(main_stream)                                   # fork
         branch_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
@@ -431,6 +475,8 @@ class Engine:
             up = empty((B, 2 * a.shape[1], 2 * a.shape[2], 2 * a.shape[3], a.shape[4]))
             return ops.upsample2_fwd(a, up)
 
+        if pack_ev is not None:
+            torch.cuda.current_stream(dev).wait_event(pack_ev)
         attnout = upconv("deep_conv", attnall)
         at1 = upconv("up1", attnout)
         at2 = upconv("up2", at1)
@@ -448,6 +494,8 @@ class Engine:
         # GEMMs have the GPU to themselves instead of queueing behind the 41 k blocks of the first encoder kernels.
         for ev in pe_events:
             main_stream.wait_event(ev)
+        if pack_ev is not None:
+            main_stream.wait_event(pack_ev)
         if self.use_tc and self.use_stem and dtype == torch.bfloat16 and ops.stem_supported(M, nf):
             xcl = ops.stem_im2col(x)        # first conv = one GEMM over the gathered taps (csrc/tc_conv.cu, stem path)
         else:

@@ -218,9 +218,12 @@ class GraphedTrainStep:
 
     def step(self, data: torch.Tensor, target: torch.Tensor):
         if self._staged is not None and self._staged[0] is data and self._staged[1] is target:
-            torch.cuda.current_stream().wait_event(self._staged[2])     # H2D of this batch was prefetched
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staged[2])     # H2D of this batch was prefetched
             self.x.copy_(self._sx)
             self.t.copy_(self._st)
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record(cur)      # the staging buffers may be overwritten from here on (NOT after the whole step)
             self._staged = None
         else:
             self.x.copy_(data, non_blocking=True)
@@ -235,7 +238,13 @@ class GraphedTrainStep:
             self._copy_stream = torch.cuda.Stream(device=self.x.device)
             self._sx, self._st = torch.empty_like(self.x), torch.empty_like(self.t)
         cs = self._copy_stream
-        cs.wait_stream(torch.cuda.current_stream())     # staging buffers are free once the previous step consumed them
+        # staging buffers are free once the previous step's device-side copy consumed them: wait for THAT copy, not for
+        # the whole step that was enqueued behind it (otherwise the H2D transfer never overlaps the step's kernels)
+        free_ev = getattr(self, "_staging_free", None)
+        if free_ev is not None:
+            cs.wait_event(free_ev)
+        else:
+            cs.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cs):
             self._sx.copy_(data, non_blocking=True)
             self._st.copy_(target, non_blocking=True)
