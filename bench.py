@@ -151,6 +151,11 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    # stdout carries exactly ONE JSON line: anything native libraries print there meanwhile (NCCL's version banner)
+    # is sent to stderr by pointing fd 1 at fd 2 until the result line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     from oracle import hdf_oracle as O   # only for synthetic data generation + the cpu_baseline leg
     from hdenseformer_b200 import _C, trainer as T
@@ -316,6 +321,8 @@ def main():
             out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "volumes/s", "cores": threads, "kind": "port",
                                    "sample": f"{n} step(s) of BASELINE config[0] (1x2x96^3 fwd+loss+bwd, fp32, train mode) on "
                                              f"{threads} host threads; oracle/hdf_oracle.py"}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
         # a captured graph holds NCCL kernels; tearing the communicator down underneath it can hang, so leave
