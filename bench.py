@@ -121,6 +121,8 @@ def main():
     ap.add_argument("--batch", type=int, default=2, help="volumes per GPU per step (reference BATCH_SIZE=2, config.py:77)")
     ap.add_argument("--size", type=int, nargs=3, default=[144, 144, 144])
     ap.add_argument("--depth", type=int, default=12)
+    ap.add_argument("--modalities", type=int, default=2, help="input channels (2 = PET/CT headline config; 3/4 = MR configs)")
+    ap.add_argument("--classes", type=int, default=2)
     ap.add_argument("--fp32", action="store_true", help="exact fp32 path instead of bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
@@ -130,8 +132,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     warmup = max(a.warmup, int(os.environ.get("HDF_BENCH_MIN_WARMUP", 3)))   # timing rule: W >= 3 (env override only for ncu runs)
-    workload = f"HDenseFormer_32 3D train step, PET/CT {a.batch}x2x{size[0]}x{size[1]}x{size[2]} per GPU, td={a.depth}, " \
-               f"DeepSuperloss(CEPlusDice), Adam"
+    kind = "PET/CT" if a.modalities == 2 else f"{a.modalities}-modality MR"
+    workload = f"HDenseFormer_32 3D train step, {kind} {a.batch}x{a.modalities}x{size[0]}x{size[1]}x{size[2]} per GPU, " \
+               f"td={a.depth}, " + (f"n_cls={a.classes}, " if a.classes != 2 else "") + "DeepSuperloss(CEPlusDice), Adam"
     gf_step = 3.0 * FWD_GF_PER_SAMPLE.get(size, 1410.6 * (size[0] * size[1] * size[2]) / 144 ** 3)   # per sample
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
@@ -169,7 +172,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hdf_bench_nccl_%h_%p.log")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    net = HDenseFormer_32(2, 2, size, a.depth).to(dev).train()
+    net = HDenseFormer_32(a.modalities, a.classes, size, a.depth).to(dev).train()
     with torch.no_grad():
         for k, p in net.named_parameters():
             if k.endswith("position_embeddings"):
@@ -182,7 +185,9 @@ def main():
                            fused=True, capturable=use_graph)   # grouping of trainer.py:812-819
     dp = T.DataParallelTrainer(net, crit, opt, use_bf16=not a.fp32)
     nb = 2   # two distinct pinned batches, alternated
-    host = [(O.synth_petct(a.batch, size, seed=rank * 10 + i).pin_memory(), O.synth_label(a.batch, 2, size, seed=rank * 10 + i).pin_memory())
+    synth_x = (lambda sd_: O.synth_petct(a.batch, size, seed=sd_)) if a.modalities == 2 else \
+              (lambda sd_: O.synth_mr(a.batch, a.modalities, size, seed=sd_))
+    host = [(synth_x(rank * 10 + i).pin_memory(), O.synth_label(a.batch, a.classes, size, seed=rank * 10 + i).pin_memory())
             for i in range(nb)]
     devb = [(x.to(dev), t.to(dev)) for x, t in host]
 
