@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--classes", type=int, default=2)
     ap.add_argument("--fp32", action="store_true", help="exact fp32 path instead of bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused=True) instead of the library's FusedAdam")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
     size = tuple(a.size)
@@ -181,8 +182,12 @@ def main():
     decay = [p for n_, p in net.named_parameters() if p.dim() > 1 and not n_.endswith(".bias")]
     no_decay = [p for n_, p in net.named_parameters() if not (p.dim() > 1 and not n_.endswith(".bias"))]
     use_graph = not a.no_graph and (world == 1 or os.environ.get("HDF_BENCH_GRAPH_MULTI", "1") == "1")
-    opt = torch.optim.Adam([{"params": decay, "weight_decay": 1e-4}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-3,
-                           fused=True, capturable=use_graph)   # grouping of trainer.py:812-819
+    if a.torch_adam:
+        opt = torch.optim.Adam([{"params": decay, "weight_decay": 1e-4}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-3,
+                               fused=True, capturable=use_graph)   # grouping of trainer.py:812-819
+    else:
+        from hdenseformer_b200.optim import FusedAdam              # one launch over the gradient arena, same grouping
+        opt = FusedAdam(net, lr=1e-3, weight_decay=1e-4)
     dp = T.DataParallelTrainer(net, crit, opt, use_bf16=not a.fp32)
     nb = 2   # two distinct pinned batches, alternated
     synth_x = (lambda sd_: O.synth_petct(a.batch, size, seed=sd_)) if a.modalities == 2 else \

@@ -200,6 +200,17 @@ int hdf_sw_accumulate(int dtype, const void* logits, float* agg, int C, int X, i
 int hdf_sw_finalize(float* agg, long long* mask, int C, int X, int Y, int Z, const int* steps_x, int nx, const int* steps_y,
                     int ny, const int* steps_z, int nz, int patch_x, int patch_y, int patch_z, int normalise, void* stream);
 
+/* ---- fused Adam / AdamW over the flat gradient arena (reference: trainer.py:793-840 optimizer selection with no weight
+ *      decay for 1-D parameters and biases).  The table (one entry per parameter tensor) is packed on the host with
+ *      hdf_adam_table_set and uploaded by the caller; chunks is a device int2 array (tensor index, chunk index), one CTA
+ *      per hdf_adam_chunk() elements; hyper is a device float[2] {learning rate, step count} so that graph replays see
+ *      scheduler updates; grad_scale multiplies the gradient (1/world for a summed all-reduce, 1 otherwise). ---- */
+size_t hdf_adam_table_bytes(int ntensors);
+int hdf_adam_chunk(void);
+int hdf_adam_table_set(void* host_table, int index, float* param, long long offset, long long n, float weight_decay);
+int hdf_adam_step(const void* table, const void* chunks, int nchunks, const float* grad_flat, float* m_flat, float* v_flat,
+                  float* hyper, float beta1, float beta2, float eps, int adamw, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

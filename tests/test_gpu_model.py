@@ -199,3 +199,44 @@ def test_bf16_tensor_core_path_other_configs(in_ch, n_cls, size, batch):
         cos.append((a @ b).item() / max(a.norm().item() * b.norm().item(), 1e-30))
     # yardstick (SURVEY 8c pitfall 3): the reference's own bf16 autocast reaches min cosine 0.926 vs fp64 on such sizes
     assert min(cos) > 0.90 and sum(cos) / len(cos) > 0.98, (min(cos), sum(cos) / len(cos))
+
+
+@pytest.mark.parametrize("adamw", [False, True])
+def test_fused_adam_matches_torch(adamw):
+    """FusedAdam over the gradient arena == torch.optim.Adam/AdamW with the reference's no-decay grouping
+    (trainer.py:812-819): 5 steps on identical prescribed gradients (model-produced gradients would feed 1-ulp
+    differences back through Adam's normalisation and make the trajectories incomparable), including a learning-rate
+    change through param_groups; then one real training step through the trainer API."""
+    from hdenseformer_b200.optim import FusedAdam
+    size = (32, 32, 32)
+    ma, _ = build(2, 2, 8, size, 4)
+    mb, _ = build(2, 2, 8, size, 4)
+    oa = FusedAdam(ma, lr=1e-3, weight_decay=1e-2, adamw=adamw)
+    decay = [p for n, p in mb.named_parameters() if p.dim() > 1 and not n.endswith(".bias")]
+    nodec = [p for n, p in mb.named_parameters() if not (p.dim() > 1 and not n.endswith(".bias"))]
+    cls = torch.optim.AdamW if adamw else torch.optim.Adam
+    ob = cls([{"params": decay, "weight_decay": 1e-2}, {"params": nodec, "weight_decay": 0.0}], lr=1e-3)
+    arena = ma._grad_arena()
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    for it in range(5):
+        if it == 2:
+            for g in oa.param_groups: g["lr"] = 5e-4
+            for g in ob.param_groups: g["lr"] = 5e-4
+        for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            g = torch.randn(pa.shape, device=DEV, generator=gen) * (10.0 ** float(torch.randint(-6, 1, (1,)).item()))
+            arena.views[k].copy_(g)
+            pb.grad = g.clone()
+        oa.step()
+        ob.step()
+    worst, wk = 0.0, None
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        e = ((pa - pb).abs().max() / pb.abs().max().clamp_min(1e-12)).item()
+        if e > worst:
+            worst, wk = e, k
+    assert worst < 5e-6, (wk, worst)
+    # and through the trainer API on real gradients: the loss must go down
+    ma.eval()
+    crit = DeepSuperloss(CEPlusDice(ignore_index=0))
+    x, t = O.synth_petct(2, size, seed=9), O.synth_label(2, 2, size, seed=9)
+    losses = [T.train_step(ma, crit, oa, x, t, use_bf16=False).item() for _ in range(5)]
+    assert losses[-1] < losses[0], losses
