@@ -128,3 +128,18 @@ def test_grad_bucketer_and_patch_merge_world2_gloo():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(60) for p in ps]
     assert res == [(0, True), (1, True)]
+
+
+def test_fused_adam_and_stem_have_no_cpu_path_and_pure_helpers_answer_without_a_gpu():
+    """Entry points that need no device answer on the CPU box (planning helpers); the optimizer refuses a CPU model."""
+    from hdenseformer_b200.optim import FusedAdam
+    lib = _C.load()
+    assert lib.hdf_stem_kp(1) == 64 and lib.hdf_stem_kp(2) == 64 and lib.hdf_stem_kp(3) == 128 and lib.hdf_stem_kp(4) == 128
+    assert lib.hdf_stem_kp(5) == 0 and lib.hdf_stem_supported(2, 32) == 1 and lib.hdf_stem_supported(2, 48) == 0
+    assert lib.hdf_adam_chunk() > 0 and lib.hdf_adam_table_bytes(3) == 3 * lib.hdf_adam_table_bytes(1)
+    buf = ctypes.create_string_buffer(lib.hdf_adam_table_bytes(2))
+    assert lib.hdf_adam_table_set(buf, 1, 4096, 128, 10, 0.5) == 0
+    assert lib.hdf_adam_table_set(buf, 0, 0, 0, 10, 0.0) != 0 and "hdf_adam_table_set" in _C.last_error()   # null param
+    m = HDenseFormer(2, 2, 8, (32, 32, 32), 4)
+    with pytest.raises(RuntimeError):
+        FusedAdam(m, lr=1e-3)
