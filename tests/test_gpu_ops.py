@@ -361,3 +361,24 @@ def test_upsample_cell_kernel_odd_sizes_and_channel_slices():
         got = buf[..., :C].float().permute(0, 4, 1, 2, 3)
         assert rel(got, ref) < TOL[torch.bfloat16]
         assert (buf[..., C:] == 5.0).all()
+
+
+def test_upsample_bwd_odd_sizes_slices_and_accumulate():
+    """bf16 trilinear x2 backward (csrc/glue.cu; gather form by default, separable form with HDF_UPS_BWD_V2=1) vs torch
+    autograd: odd sizes, size-1 dims, channel-slice operands, overwrite and accumulate modes."""
+    torch.manual_seed(12)
+    for size, C in [((3, 5, 7), 32), ((1, 1, 9), 16), ((2, 9, 1), 64), ((4, 6, 8), 8)]:
+        x = torch.randn(2, C, *size, device=DEV, requires_grad=True)
+        up = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+        gfull = torch.randn(2, 2 * size[0], 2 * size[1], 2 * size[2], C + 8, device=DEV).to(torch.bfloat16)
+        g = gfull[..., 4:4 + C]                                    # channel slice (ld != C)
+        up.backward(g.float().permute(0, 4, 1, 2, 3))
+        ref = x.grad.permute(0, 2, 3, 4, 1)
+        buf = torch.full((2, *size, C + 16), 3.0, dtype=torch.bfloat16, device=DEV)
+        ops.upsample2_bwd(g, buf[..., 8:8 + C], False)
+        assert rel(buf[..., 8:8 + C].float(), ref) < TOL[torch.bfloat16]
+        assert (buf[..., :8] == 3.0).all() and (buf[..., 8 + C:] == 3.0).all()
+        base = torch.randn(2, *size, C, device=DEV).to(torch.bfloat16)
+        acc = base.clone()
+        ops.upsample2_bwd(g, acc, True)
+        assert rel(acc.float(), base.float() + ref) < 2 * TOL[torch.bfloat16]
