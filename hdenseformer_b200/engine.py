@@ -235,7 +235,7 @@ class Engine:
         dy = ops.instnorm_bwd(dout, y, mean, rstd, g, b, G[f"{name}.norm.weight"] if affine else None,
                               G[f"{name}.norm.bias"] if affine else None, relu=True)
         if self.defer_wgrad and self._defer_open:
-            self._deferred.append((x, dy, G[wkey], 0))
+            self._deferred.append((x, dy, G[wkey], 0, wkey))
         else:
             self._conv_wgrad(x, dy, G[wkey])
         if bias:
@@ -564,7 +564,7 @@ class Engine:
             da = empty(a_in.shape)
             self._conv_dgrad(du, P[name + ".weight"], da, mode=1)
             if self.defer_wgrad and self._defer_open:
-                self._deferred.append((a_in, du, G[name + ".weight"], 1))
+                self._deferred.append((a_in, du, G[name + ".weight"], 1, name + ".weight"))
             else:
                 self._conv_wgrad(a_in, du, G[name + ".weight"], mode=1)
             ops.colsum(du, G[name + ".bias"])
@@ -641,8 +641,19 @@ class Engine:
         self._defer_open = False
         dA = self._cnr_bwd(c, "block_1_2_left", dds0, P, G)
         self._cnr_bwd(c, "block_1_1_left", dA, P, G, need_dx=False)
-        for (wx, wdy, wg, wmode) in self._deferred:
+        # Gradient buckets for the data-parallel all-reduce: everything except the transformer branches is final once the
+        # deferred weight gradients have run, and they complete in arena order, so after the j-th of them the arena
+        # prefix up to (not including) the next deferred weight is final.  The all-reduces issued here (NCCL stream,
+        # ordered behind the main stream) overlap the remaining weight gradients and the transformer backward.
+        order = list(G.keys())
+        pos = {k: i for i, k in enumerate(order)}
+        for j, (wx, wdy, wg, wmode, wkey) in enumerate(self._deferred):
             self._conv_wgrad(wx, wdy, wg, mode=wmode)
+            if side is not None:
+                nxt = self._deferred[j + 1][4] if j + 1 < len(self._deferred) else None
+                notify(order[pos[nxt] - 1] if nxt is not None else "deep_conv.double_conv.0.bias")
+        if not self._deferred and side is not None:
+            notify("deep_conv.double_conv.0.bias")
         self._deferred = []
         if side is None:
             notify("deep_conv.double_conv.0.bias")

@@ -8,6 +8,28 @@ import torch
 from .. import ops
 
 
+_CW_CACHE = {}
+
+
+def _device_weight(cw: Optional[torch.Tensor], dev) -> Optional[torch.Tensor]:
+    """fp32 device copy of the class weights, made once per (tensor, version, device): the reference keeps the weight
+    as a plain CPU tensor attribute (trainer.py:743-744; not a registered buffer), and a fresh pageable-host -> device
+    copy on every step would synchronise the stream and cannot be captured in a CUDA graph."""
+    if cw is None:
+        return None
+    cw = cw.detach()
+    if cw.device == dev and cw.dtype == torch.float32 and cw.is_contiguous():
+        return cw
+    key = (cw.data_ptr(), cw._version, tuple(cw.shape), str(cw.dtype), str(dev))
+    hit = _CW_CACHE.get(key)
+    if hit is None:
+        if len(_CW_CACHE) > 16:
+            _CW_CACHE.clear()
+        hit = (cw, cw.to(device=dev, dtype=torch.float32).contiguous())     # keep the source alive: data_ptr stays unique
+        _CW_CACHE[key] = hit
+    return hit[1]
+
+
 class _SegLossFn(torch.autograd.Function):
     """loss = sum_i level_weight_i * (ce_w * CE(pred_i, nearest(target)) + dice_w * Dice(pred_i, nearest(target)))."""
 
@@ -21,7 +43,7 @@ class _SegLossFn(torch.autograd.Function):
         per_level = torch.zeros((len(preds), 3), dtype=torch.float32, device=dev)
         sums: List[torch.Tensor] = []
         target = target.detach().float().contiguous()
-        cwd = None if cw is None else cw.detach().to(device=dev, dtype=torch.float32).contiguous()
+        cwd = _device_weight(cw, dev)
         ps = []
         for i, p in enumerate(preds):
             p = p.detach()

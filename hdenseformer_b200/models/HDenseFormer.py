@@ -92,12 +92,20 @@ class _HDFFunction(torch.autograd.Function):
     def backward(ctx, *gouts):
         m = ctx.module
         arena = m._grad_arena()
+        # `.grad` tensors are views of the arena.  If some parameter still holds such a view, the arena carries live
+        # gradients of an earlier backward that nobody cleared (gradient accumulation, or the model called twice in one
+        # autograd graph): keep them aside and add them back, instead of silently wiping them.
+        live = any(prm.grad is not None and prm.grad.data_ptr() == arena.views[k].data_ptr() for k, prm in ctx.P.items())
+        carried = arena.flat.clone() if live else None
         arena.zero_()
-        m._engine.backward(ctx.P, arena.views, ctx.saved, list(gouts), on_grads_ready=m._on_grads_ready)
+        m._engine.backward(ctx.P, arena.views, ctx.saved, list(gouts), on_grads_ready=None if live else m._on_grads_ready)
+        if carried is not None:
+            arena.flat.add_(carried)
+            m._on_grads_ready(list(arena.views)[-1])      # data-parallel hook: everything is final only now
         ctx.saved = None
         # Hand the gradients over as views of the arena instead of returning them to autograd: AccumulateGrad would clone
         # every view into its own storage (406 device-to-device copies of ~1.5 us each, serial, at the tail of every step:
-        # profiles/r1_timeline_v17.txt).  Accumulation into a foreign .grad tensor is still honoured.
+        # profiles/r1_timeline_v17.txt).  A foreign `.grad` tensor (not an arena view) is accumulated into.
         for k, prm in ctx.P.items():
             if not prm.requires_grad:
                 continue

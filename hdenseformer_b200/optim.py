@@ -3,8 +3,11 @@ with the no-decay grouping of `trainer.py:812-819`: parameters with fewer than 2
 
 One kernel launch updates every parameter from the model's flat gradient arena (csrc/optim.cu); moments are flat fp32
 buffers with the arena's offsets.  Learning rate and step count live on the device, so a captured training step can be
-replayed while a scheduler changes the rate (`set_lr`).  Duck-types the parts of `torch.optim.Optimizer` the reference
-trainer uses: `step()`, `zero_grad(set_to_none=True)`, `param_groups[i]['lr']`, `state_dict()` / `load_state_dict()`."""
+replayed while a scheduler changes the rate.  It IS a `torch.optim.Optimizer` (two parameter groups: decayed / not
+decayed), so `torch.optim.lr_scheduler.*` and the reference's `PolyLR` (trainer.py:263-264, 1012-1032) accept it: they
+write `param_groups[i]['lr']` on the host, `step()` (eager) and `GraphedTrainStep.step()` (before every replay, through
+`sync_lr()`) push that value to the device-resident rate.  Both groups share one rate (the reference never uses
+per-group rates)."""
 from __future__ import annotations
 
 import ctypes
@@ -16,7 +19,7 @@ from . import _C
 from .ops import _p, _s, ensure_init
 
 
-class FusedAdam:
+class FusedAdam(torch.optim.Optimizer):
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  adamw: bool = False, no_decay_1d: bool = True):
         self.model = model
@@ -35,8 +38,10 @@ class FusedAdam:
 
         decay = [p for k, p in named if wd_of(k, p) > 0]
         no_decay = [p for k, p in named if wd_of(k, p) == 0]
-        self.param_groups = [{"params": decay, "lr": float(lr), "weight_decay": float(weight_decay)},
-                             {"params": no_decay, "lr": float(lr), "weight_decay": 0.0}]
+        groups = [{"params": decay, "weight_decay": float(weight_decay)}, {"params": no_decay, "weight_decay": 0.0}]
+        groups = [g for g in groups if g["params"]]
+        torch.optim.Optimizer.__init__(self, groups, dict(lr=float(lr), betas=self.betas, eps=self.eps,
+                                                          weight_decay=float(weight_decay)))
         chunk = lib.hdf_adam_chunk()
         host_tab = ctypes.create_string_buffer(lib.hdf_adam_table_bytes(len(named)))
         chunks = []
@@ -64,19 +69,18 @@ class FusedAdam:
         self.hyper[0:1].fill_(float(lr))
         self._lr_uploaded = float(lr)
 
-    def zero_grad(self, set_to_none: bool = True):
-        for g in self.param_groups:
-            for p in g["params"]:
-                if set_to_none:
-                    p.grad = None
-                elif p.grad is not None:
-                    p.grad.zero_()
+    def sync_lr(self):
+        """Push a learning rate written to `param_groups[..]['lr']` (LR schedulers do that) to the device copy."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_uploaded:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedAdam: learning rate changed while capturing a CUDA graph; call sync_lr() before")
+            self.set_lr(lr)
 
     @torch.no_grad()
     def step(self, closure=None):
-        lr = float(self.param_groups[0]["lr"])
-        if lr != self._lr_uploaded and not torch.cuda.is_current_stream_capturing():
-            self.set_lr(lr)            # a scheduler wrote param_groups[...]['lr']
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()             # a scheduler wrote param_groups[...]['lr']
         arena = self.model._grad_arena()
         if arena is not self.arena:
             raise RuntimeError("FusedAdam: the model's gradient arena was re-created (device change?); build a new optimizer")

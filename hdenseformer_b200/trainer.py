@@ -82,19 +82,26 @@ def _graphed_forward(net, shape, use_bf16):
     # the graph bakes in parameter addresses, not values: it stays valid across optimizer steps / load_state_dict
     key = (id(net), tuple(shape), bool(use_bf16), tuple(p.data_ptr() for p in list(net.parameters())[:4]))
     if key not in _FWD_CACHE:
+        while len(_FWD_CACHE) >= 4:          # bounded: graphs pin their static buffers and every saved activation
+            _FWD_CACHE.pop(next(iter(_FWD_CACHE)))
         _FWD_CACHE[key] = _GraphedForward(net, shape, use_bf16)
     return _FWD_CACHE[key]
 
 
 @torch.no_grad()
 def inference_slidingwindow(net, image, n_cls: int, patch_size: Sequence[int], step_size: Sequence[int],
-                            use_bf16: bool = False, group=None, return_prob: bool = False, use_graph: bool = False):
+                            use_bf16: bool = False, group=None, return_prob: bool = False, use_graph: bool = False,
+                            patch_batch: int = 1):
     """Sliding-window inference of one volume `image` [M, X, Y, Z] (numpy or tensor, host or device).
 
     Every rank of `group` (or the single process) evaluates its share of the patches and accumulates
     softmax probabilities into a private fp32 buffer; the buffers are summed with one all-reduce, then
     normalised by the analytic per-voxel window count and arg-maxed on device.  Returns the int64 mask
-    [X, Y, Z] on the device (and the averaged probabilities if return_prob)."""
+    [X, Y, Z] on the device (and the averaged probabilities if return_prob).
+
+    `patch_batch` > 1 evaluates that many patches per forward call (the reference loops with batch 1,
+    trainer.py:530-577; InstanceNorm, LayerNorm and attention are per-sample, so the results do not change, while a
+    batch-1 forward is latency-bound on a B200)."""
     from . import ops
     dev = next(net.parameters()).device
     if isinstance(image, np.ndarray):
@@ -115,17 +122,19 @@ def inference_slidingwindow(net, image, n_cls: int, patch_size: Sequence[int], s
     px, py, pz = patch_size
     if image.device != dev and not image.is_pinned():
         image = image.pin_memory() if torch.cuda.is_available() else image
-    fwd = _graphed_forward(net, (1, M, px, py, pz), use_bf16) if use_graph else None
-    for (x, y, z) in mine:
-        data = image[None, :, x:x + px, y:y + py, z:z + pz].to(dev, non_blocking=True).contiguous()
-        if fwd is not None:
-            logits = fwd(data)
+    patch_batch = max(1, int(patch_batch))
+    for g0 in range(0, len(mine), patch_batch):
+        grp = mine[g0:g0 + patch_batch]
+        data = torch.stack([image[:, x:x + px, y:y + py, z:z + pz] for (x, y, z) in grp]).to(dev, non_blocking=True).contiguous()
+        if use_graph:
+            logits = _graphed_forward(net, (len(grp), M, px, py, pz), use_bf16)(data)
         elif use_bf16:
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 logits = net(data)[0]
         else:
             logits = net(data)[0]
-        ops.sw_accumulate(logits.contiguous(), agg, x, y, z)
+        for j, (x, y, z) in enumerate(grp):
+            ops.sw_accumulate(logits[j:j + 1].contiguous(), agg, x, y, z)
     if world > 1:
         dist.all_reduce(agg, op=dist.ReduceOp.SUM, group=group)
     mask = ops.sw_finalize(agg, steps, list(patch_size), normalise=return_prob)
@@ -228,6 +237,9 @@ class GraphedTrainStep:
         else:
             self.x.copy_(data, non_blocking=True)
             self.t.copy_(target, non_blocking=True)
+        sync_lr = getattr(self.optimizer, "sync_lr", None)
+        if sync_lr is not None:
+            sync_lr()        # an LR scheduler writes param_groups[..]['lr'] on the host; the replayed step reads the device copy
         self.graph.replay()
         return self.loss
 
@@ -265,6 +277,7 @@ class GradBucketer:
         self.prev = 0
         self.works = []
         self.ranges: List[Tuple[int, int]] = []
+        self.last_ranges: List[Tuple[int, int]] = []
 
     def notify(self, end: int, force: bool = False):
         if end - self.prev < self.min_bucket and not force:
@@ -291,6 +304,7 @@ class GradBucketer:
                 w.wait()
         self.works = []
         self.prev = 0
+        self.last_ranges, self.ranges = self.ranges, []      # buckets issued during the step that just finished
 
 
 class DataParallelTrainer:

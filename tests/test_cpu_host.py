@@ -46,7 +46,9 @@ def test_state_dict_matches_reference_table(golden_dir):
                                                             tuple(meta["image_size"]), meta["transformer_depth"])))
     # headline config: 406 tensors, 11.074 M parameters
     t = param_table(2, 2, 32, (144, 144, 144), 12)
-    assert len(t) == 406 and sum(int(np.prod(s)) for s in t.values()) == 11073928 or len(t) == 406
+    assert len(t) == 406 and sum(int(np.prod(s)) for s in t.values()) == 11073992
+    t24 = param_table(2, 2, 32, (144, 144, 144), 24)       # shipped default depth (config.py:120): 11.561 M
+    assert len(t24) == 742 and sum(int(np.prod(s)) for s in t24.values()) == 11561288
     assert HDenseFormer_16(2, 2, (32, 32, 32), 4).n_filters == 16
     assert HDenseFormer_32(2, 2, (32, 32, 32), 4).n_filters == 32
 
@@ -104,7 +106,7 @@ def _bucket_worker(rank, world, port, q):
     gathered = [torch.zeros(1000) for _ in range(world)]
     dist.all_gather(gathered, mine)
     expect = sum(gathered) / world
-    ok = torch.allclose(flat, expect, atol=1e-6) and b.ranges == [(0, 250), (250, 900), (900, 1000)]
+    ok = torch.allclose(flat, expect, atol=1e-6) and b.last_ranges == [(0, 250), (250, 900), (900, 1000)] and b.ranges == []
     # sliding-window merge: each rank accumulates its own patches, all-reduce(sum) == serial result
     steps = T.cal_steps((20, 20, 20), (16,) * 3, (8,) * 3)
     agg = torch.zeros(20, 20, 20)

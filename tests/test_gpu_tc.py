@@ -26,6 +26,11 @@ CASES = [
     (256, 128, (9, 9, 9), 1),        # 4 K-chunks
     (128, 256, (4, 6, 10), 2),       # N = 256 (TMEM 512 cols)
     (48, 80, (5, 7, 11), 1),         # KC = 16 with 3 chunks, odd N
+    (256, 256, (9, 9, 9), 2),        # block_4_2_left / deep_conv at nf=32 (the benchmarked model): 9^3 token grid, B=2
+    (256, 256, (18, 18, 18), 1),     # block_4_2_left @144^3
+    (512, 256, (9, 9, 9), 1),        # deep_conv with 4 modalities (BASELINE config 4)
+    (32, 32, (24, 20, 36), 2),       # full-resolution 32->32 layers (fold + kh-fold plan), ragged W
+    (64, 32, (16, 12, 40), 1),       # block_1_1_right shape class
 ]
 
 
@@ -86,6 +91,9 @@ WG_CASES = [
     (128, 128, (6, 10, 12), 1),   # 7 passes
     (256, 128, (9, 9, 9), 1),     # two 128-channel groups per tap
     (128, 256, (4, 6, 10), 2),    # KV = 64 chunks, N = 256
+    (256, 256, (9, 9, 9), 2),     # block_4_2_left / deep_conv at nf=32
+    (256, 256, (18, 18, 18), 1),
+    (512, 256, (9, 9, 9), 1),     # deep_conv with 4 modalities
 ]
 
 
