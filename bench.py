@@ -2,14 +2,20 @@
 """Headline benchmark: HDenseFormer_32 3D training step at 2x144^3 (BASELINE.json configs[1]).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU restatement of the reference
-                                                             # (oracle/) timed on the host cores, rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the UNMODIFIED reference module staged in
+                                                             # oracle/_ref (oracle/stage_ref.py; the functional port in
+                                                             # oracle/hdf_oracle.py if absent) on the host cores, rank 0
 
 Prints ONE JSON line (rank 0).  A "step" = forward (bf16) + Dice/CE deep-supervision loss + backward + gradient
 all-reduce (N>1) + Adam step on one synthetic batch of `--batch` volumes per GPU.
   value : volumes/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e   : same metric through the public API (trainer.train_step) from PINNED HOST batches, H2D inside the timed
           region and a D2H read of the loss every step
+  roofline           : all tcgen05 convolution launches of the step (forward / input-gradient / weight-gradient classes,
+                       each layer timed alone with CUDA events) against the measured bf16 peak, plus the largest layer
+  sliding_window     : the metric's second half -- ms per 2 x 224^3 volume (27 patches of 144^3, patches sharded over the
+                       N ranks, 2 patches per forward), Dice of the bf16 mask against the reference's fp32 mask
+  gpu_eager_baseline : the reference module itself, eager cuDNN/cuBLAS under bf16 autocast, train mode, same GPU
 """
 from __future__ import annotations
 
@@ -82,22 +88,40 @@ class ClockSampler:
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_step_time(size, batch, td, steps, warmup, budget_s):
-    """Times the CPU restatement of the reference (oracle/hdf_oracle.py): fwd + DeepSuperloss(CEPlusDice) + backward,
-    fp32, train-mode dropout on, all host threads.  Returns (seconds/step, steps actually timed, threads)."""
+def cpu_reference_step_time(size, batch, td, steps, warmup, budget_s, modalities=2, classes=2):
+    """Times the reference's own CPU implementation of the path: fwd + DeepSuperloss(CEPlusDice(ignore_index=0)) + zero_grad
+    + backward (trainer.py:369-374), fp32, train mode (dropout on), all host threads.  Uses the unmodified reference modules
+    staged in oracle/_ref (kind "reference"); falls back to the functional port oracle/hdf_oracle.py (kind "port").
+    Returns (seconds/step, steps timed, threads, kind)."""
     from oracle import hdf_oracle as O
+    from oracle import stage_ref
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    shapes = O.param_shapes(2, 2, 32, size, td)
-    sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(shapes, seed=0).items()}
-    x, t = O.synth_petct(batch, size, seed=0), O.synth_label(batch, 2, size, seed=0)
-    g = torch.Generator().manual_seed(0)
+    x = O.synth_petct(batch, size, seed=0) if modalities == 2 else O.synth_mr(batch, modalities, size, seed=0)
+    t = O.synth_label(batch, classes, size, seed=0)
+    ref = stage_ref.load()
+    if ref is not None:
+        kind = "reference"
+        torch.manual_seed(0)
+        net = ref[0](modalities, classes, size, td).train()
+        crit = ref[3](ref[2](weight=None, ignore_index=0))
 
-    def one():
-        for v in sd.values():
-            v.grad = None
-        outs = O.forward(sd, x, td, dropout_p=0.5, generator=g)
-        O.deep_super_loss(outs, t, ignore_index=0).backward()
+        def one():
+            out = net(x)
+            loss = crit(out, t)
+            net.zero_grad(set_to_none=True)
+            loss.backward()
+    else:
+        kind = "port"
+        shapes = O.param_shapes(modalities, classes, 32, size, td)
+        sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(shapes, seed=0).items()}
+        g = torch.Generator().manual_seed(0)
+
+        def one():
+            for v in sd.values():
+                v.grad = None
+            outs = O.forward(sd, x, td, dropout_p=0.5, generator=g)
+            O.deep_super_loss(outs, t, ignore_index=0).backward()
 
     t0 = time.perf_counter()
     one()
@@ -109,7 +133,58 @@ def cpu_reference_step_time(size, batch, td, steps, warmup, budget_s):
     t0 = time.perf_counter()
     for _ in range(n):
         one()
-    return (time.perf_counter() - t0) / n, n, threads
+    return (time.perf_counter() - t0) / n, n, threads, kind
+
+
+CONV_LAYERS = [  # name, Cin, Cout, spatial divisor, mode (0 conv, 1 transposed conv: divisor = OUTPUT resolution)
+    ("block_1_2_left", 1, 1, 1, 0), ("block_2_1_left", 1, 2, 2, 0), ("block_2_2_left", 2, 2, 2, 0),
+    ("block_3_1_left", 2, 4, 4, 0), ("block_3_2_left", 4, 4, 4, 0), ("block_4_1_left", 4, 8, 8, 0),
+    ("block_4_2_left", 8, 8, 8, 0), ("upconv_3", 8, 4, 4, 1), ("block_3_1_right", 8, 4, 4, 0),
+    ("block_3_2_right", 4, 4, 4, 0), ("upconv_2", 4, 2, 2, 1), ("block_2_1_right", 4, 2, 2, 0),
+    ("block_2_2_right", 2, 2, 2, 0), ("upconv_1", 2, 1, 1, 1), ("block_1_1_right", 2, 1, 1, 0),
+    ("block_1_2_right", 1, 1, 1, 0), ("deep_conv", None, 8, 16, 0), ("up1", 8, 4, 8, 0), ("up2", 4, 2, 4, 0),
+    ("up3", 2, 1, 2, 0)]     # channel counts in units of n_filters (deep_conv input = 4*nf*modalities)
+
+
+def conv_class_roofline(ops, batch, size, modalities, dev, timed, pk, nf=32):
+    """Every 3x3x3 convolution / transposed convolution of the model except the 2-channel stem, each launch timed alone
+    with CUDA events (inputs of the large layers exceed L2), grouped by kernel class."""
+    tot = {"fwd": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}     # [flop, ms]
+    best = None
+    D, H, W = size
+    for name, ci_u, co_u, div, mode in CONV_LAYERS:
+        ci = 4 * nf * modalities if ci_u is None else ci_u * nf
+        co = co_u * nf
+        od, oh, ow = D // div, H // div, W // div
+        idm = (od // 2, oh // 2, ow // 2) if mode == 1 else (od, oh, ow)
+        x = torch.randn(batch, *idm, ci, device=dev).to(torch.bfloat16)
+        y = torch.empty(batch, od, oh, ow, co, dtype=torch.bfloat16, device=dev)
+        g = torch.randn(batch, od, oh, ow, co, device=dev).to(torch.bfloat16)
+        dx = torch.empty_like(x)
+        flop = 2.0 * batch * od * oh * ow * (27 if mode == 0 else 27 / 8) * ci * co
+        if mode == 0:
+            w = torch.randn(co, ci, 27, device=dev) * 0.05
+            wp, wpd = ops.tc_pack(w, ci, co, 27, ci * 27, False), ops.tc_pack(w, co, ci, ci * 27, 27, True)
+            fns = {"fwd": lambda i: ops.tc_conv3d_fwd(x, wp, None, y, 0), "dgrad": lambda i: ops.tc_conv3d_fwd(g, wpd, None, dx, 0)}
+            dw = torch.empty_like(w)
+            fns["wgrad"] = lambda i: ops.tc_conv3d_wgrad(x, g, dw, 27, ci * 27, 0)
+        else:
+            w = torch.randn(ci, co, 27, device=dev) * 0.05
+            wp, wpd = ops.tc_pack(w, ci, co, co * 27, 27, False), ops.tc_pack(w, co, ci, 27, co * 27, False)
+            fns = {"fwd": lambda i: ops.tc_conv3d_fwd(x, wp, None, y, 1), "dgrad": lambda i: ops.tc_conv3d_fwd(g, wpd, None, dx, 2)}
+            dw = torch.empty_like(w)
+            fns["wgrad"] = lambda i: ops.tc_conv3d_wgrad(x, g, dw, co * 27, 27, 1)
+        for cls, fn in fns.items():
+            fn(0); fn(0)
+            ms = timed(fn, 3) / 3
+            tot[cls][0] += flop; tot[cls][1] += ms
+            if cls == "fwd" and (best is None or flop > best["algorithmic_flop_per_launch"]):
+                best = {"layer": f"{name} ({ci}->{co} @ {od}x{oh}x{ow} x{batch})", "algorithmic_flop_per_launch": flop,
+                        "ms_per_launch": ms, "achieved": flop / ms / 1e9, "frac": flop / ms / 1e9 / pk["tf_burst"]}
+        del x, y, g, dx
+    classes = {c: {"gflop": f / 1e9, "ms": ms, "achieved": f / ms / 1e9, "frac": f / ms / 1e9 / pk["tf_burst"]} for c, (f, ms) in tot.items()}
+    flop = sum(f for f, _ in tot.values()); ms = sum(m for _, m in tot.values())
+    return flop, ms, classes, best
 
 
 def main():
@@ -127,6 +202,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused=True) instead of the library's FusedAdam")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-sliding-window", action="store_true", help="skip the 2x224^3 sliding-window measurement")
+    ap.add_argument("--no-sw-dice", action="store_true", help="skip the fp32 reference mask (Dice) of the sliding-window volume")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch run of the reference module")
     a = ap.parse_args()
     size = tuple(a.size)
     rank = int(os.environ.get("RANK", 0))
@@ -142,15 +220,18 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        sec, n, threads = cpu_reference_step_time(size, 1, a.depth, a.steps, a.warmup, budget_s=150.0)
-        v = 1.0 / sec
+        sec, n, threads, kind = cpu_reference_step_time(size, a.batch, a.depth, a.steps, a.warmup, budget_s=150.0,
+                                                        modalities=a.modalities, classes=a.classes)
+        v = a.batch / sec
+        src = "unmodified reference modules (oracle/_ref: models/HDenseFormer.py, loss/*.py)" if kind == "reference" else \
+              "functional port oracle/hdf_oracle.py (oracle/_ref not staged)"
         print(json.dumps({
             "impl": "reference", "metric": "3D train volumes/sec @2x144^3", "value": v, "unit": "volumes/s", "n_gpus": a.gpus,
             "steps": n, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "note": "CPU restatement of the reference (oracle port), train mode"},
-            "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": threads, "kind": "port",
-                             "sample": f"{n} step(s) of 1x2x{size[0]}^3 fwd+loss+bwd fp32 on {threads} host threads"},
+            "config": {"workload": workload, "batch_per_gpu": a.batch, "note": f"CPU, {src}, train mode (dropout on), fwd + loss + backward"},
+            "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": threads, "kind": kind,
+                             "sample": f"{n} step(s) of {a.batch}x{a.modalities}x{size[0]}x{size[1]}x{size[2]} fwd+loss+bwd fp32 on {threads} host threads"},
             "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -286,30 +367,83 @@ def main():
     e2e = vols / (ms_e2e / 1e3)
     pk = peaks()
 
-    # ---- dominant kernel: tcgen05 conv of block_1_1_right (64 -> 32 at full resolution), timed alone with CUDA events
+    # ---- roofline of the dominant kernels: every tcgen05 convolution launch of the step (99.7 % of the step's FLOPs),
+    # each layer timed alone with CUDA events in this run, by kernel class; the largest single launch beside it
     roof = None
     if not a.fp32:
         from hdenseformer_b200 import ops
-        D, H, W = size
-        xin = torch.randn(a.batch, D, H, W, 64, device=dev).to(torch.bfloat16)     # 2x382 MB at 144^3: exceeds L2
-        wgt = torch.randn(32, 64, 3, 3, 3, device=dev) * 0.02
-        yout = torch.empty(a.batch, D, H, W, 32, dtype=torch.bfloat16, device=dev)
-        wp = ops.tc_pack(wgt, 64, 32, 27, 64 * 27, False)
-        for _ in range(3):
-            ops.tc_conv3d_fwd(xin, wp, None, yout)
-        reps = 10
-        kms = timed(lambda i: ops.tc_conv3d_fwd(xin, wp, None, yout), reps) / reps
-        flops = 2.0 * a.batch * D * H * W * 27 * 64 * 32
-        ach = flops / (kms / 1e3) / 1e12
-        # DRAM bytes per launch of this kernel from `ncu --set full` (profiles/r1_ncu_conv_fwd_b11r_final.txt:
-        # dram__bytes_read.sum 764.6 MB + dram__bytes_write.sum 365.8 MB; algorithmic 764.4 + 382.2 MB), same shape only
-        traffic = 1.1304e9 if (a.batch == 2 and size == (144, 144, 144)) else None
-        roof = {"bound": "tensor", "kernel": "tc_conv_fwd_kernel (block_1_1_right: 64->32 @ full res)", "achieved": ach,
-                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
-                "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_flop_per_launch": flops,
-                "peak_source": pk["src"] + " burst (kernel timed alone)", "ms_per_launch": kms,
+        cflop, cms, classes, best = conv_class_roofline(ops, a.batch, size, a.modalities, dev, timed, pk)
+        ach = cflop / cms / 1e9
+        # DRAM bytes of the largest launch from the committed `ncu --set full` capture of this round (same shape only)
+        traffic, traffic_src = None, None
+        tj = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+        if os.path.exists(tj) and a.batch == 2 and size == (144, 144, 144):
+            tr = json.load(open(tj))
+            traffic, traffic_src = tr.get("dram_bytes_per_launch"), tr.get("source")
+        roof = {"bound": "tensor",
+                "kernel": "tcgen05 convolution kernels (tc_conv_ws_kernel + tc_conv_fwd_kernel: forward and input gradient; "
+                          "tc_conv_wgrad_kernel: weight gradient), all 20 layers x 3 passes of one step",
+                "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
+                "algorithmic_flop_per_step": cflop, "ms_per_step_serialised": cms, "classes": classes,
+                "largest_launch": best, "traffic": traffic, "traffic_unit": "bytes/launch of largest_launch (ncu dram read+write)",
+                "traffic_source": traffic_src, "peak_source": pk["src"] + " burst (kernels timed alone)",
                 "step_frac_of_sustained_peak": (gf_step * value / 1e3) / pk["tf_sustained"]}
-        del xin, yout
+
+    # ---- the metric's second half: sliding-window inference of one 2 x 224^3 volume (BASELINE config 5), patches sharded
+    # over the ranks of this run, 2 patches per forward call, graph-replayed; Dice against the reference's fp32 mask
+    sw = None
+    if not a.fp32 and not a.no_sliding_window and size == (144, 144, 144) and a.modalities == 2 and a.classes == 2:
+        vol = O.synth_petct(1, (224, 224, 224), seed=123)[0]
+        run_sw = lambda: T.inference_slidingwindow(net, vol, 2, size, (72, 72, 72), use_bf16=True, use_graph=True, patch_batch=2)
+        mask = run_sw()
+        mask = run_sw()
+        sw_ms = timed(lambda i: run_sw(), 2) / 2
+        npatch = len(T.enumerate_patches(T.cal_steps((224, 224, 224), size, (72, 72, 72))))
+        sw = {"ms_per_volume": sw_ms, "n_gpus": world, "patches": npatch, "patch_batch": 2, "volume": "2x224x224x224",
+              "patch": list(size), "step": [72, 72, 72], "dtype": "bf16", "includes": "H2D of every patch, softmax accumulation, "
+              "all-reduce of the probability volume (N>1), normalise + argmax"}
+        if rank == 0 and not a.no_sw_dice:
+            # checker: the reference graph in fp32 (TF32 off) on the same weights, eager torch ops on this GPU
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            sdw = {k: v.detach() for k, v in net.state_dict().items()}
+            with torch.no_grad():
+                ref_mask, _ = O.sliding_window(lambda dta: O.forward(sdw, dta.to(dev), a.depth)[0].float().cpu(), vol, 2, size, (72, 72, 72))
+            sw["dice_vs_oracle_fp32_mask"] = O.mask_dice(mask.cpu(), ref_mask, 2)
+            sw["mask_mismatch_fraction"] = float((mask.cpu() != ref_mask).float().mean())
+            del sdw
+
+    # ---- like-for-like GPU comparator: the reference module itself (oracle/_ref), eager cuDNN/cuBLAS, bf16 autocast, train mode
+    eager = None
+    if rank == 0 and world == 1 and not a.fp32 and not a.no_eager_baseline:
+        try:
+            from oracle import stage_ref
+            ref = stage_ref.load()
+            if ref is not None:
+                torch.manual_seed(0)
+                rnet = ref[0](a.modalities, a.classes, size, a.depth).to(dev).train()
+                rcrit = ref[3](ref[2](weight=None, ignore_index=0))
+                ropt = torch.optim.Adam(rnet.parameters(), lr=1e-3, fused=True)
+
+                def rstep(i):
+                    x_, t_ = devb[i % nb]
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        o_ = rnet(x_)
+                    l_ = rcrit(o_, t_)
+                    ropt.zero_grad(set_to_none=True)
+                    l_.backward()
+                    ropt.step()
+
+                for i in range(2):
+                    rstep(i)
+                ems = timed(rstep, 3) / 3
+                eager = {"value": a.batch / (ems / 1e3), "unit": "volumes/s", "ms_per_step": ems,
+                         "what": "unmodified reference HDenseFormer_32 + DeepSuperloss(CEPlusDice), eager PyTorch (cuDNN/cuBLAS), "
+                                 "torch.autocast(bf16), train mode, fused Adam, same GPU, same batch"}
+                del rnet, ropt
+                torch.cuda.empty_cache()
+        except Exception as e:      # the comparator must never take the benchmark down
+            eager = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         out = {
@@ -325,12 +459,15 @@ def main():
                     "readback": "every step's loss is copied to pinned host memory and read one step later (last one inside the timed region)"},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "sliding_window": sw,
+            "gpu_eager_baseline": eager,
         }
         if world == 1 and not a.no_cpu_baseline:
-            sec, n, threads = cpu_reference_step_time((96, 96, 96), 1, a.depth, 3, 1, budget_s=25.0)
-            out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "volumes/s", "cores": threads, "kind": "port",
+            sec, n, threads, kind = cpu_reference_step_time((96, 96, 96), 1, a.depth, 3, 1, budget_s=25.0)
+            out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "volumes/s", "cores": threads, "kind": kind,
                                    "sample": f"{n} step(s) of BASELINE config[0] (1x2x96^3 fwd+loss+bwd, fp32, train mode) on "
-                                             f"{threads} host threads; oracle/hdf_oracle.py"}
+                                             f"{threads} host threads; " + ("unmodified reference modules (oracle/_ref)"
+                                                                            if kind == "reference" else "oracle/hdf_oracle.py port")}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(out), flush=True)

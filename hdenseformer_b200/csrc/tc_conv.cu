@@ -18,6 +18,7 @@
 #include "common.cuh"
 
 int hdf_sm_count_cached();
+// (weight-stationary kernel for the Cout = 32 layers: hdf_tc_ws_* in tc_conv_ws.cu, declared in hdf_b200.h)
 
 namespace {
 
@@ -71,6 +72,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// predicated forms (see umma_bf16_p): every lane of the producer warp computes the (uniform) coordinates, only the lane
+// elected at kernel start executes the instruction -- no per-lane R2UR loop around the uniform-datapath TMA instruction
+__device__ __forceinline__ void tma_load_5d_p(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                              int c4, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %8, 0;\n\t"
+      "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_p(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint32_t bar, uint32_t bytes, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(issue) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -94,6 +117,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Predicated forms for the MMA-issuing warp.  Measured on B200 (profiles/r2_umma_probe2.txt vs profiles/r1_umma_probe.txt):
+// an SS-mode M128 x N96 x K16 MMA executes in 56 clk when the issuing code keeps its operands in uniform registers, but
+// the round-1 kernels spent ~147 clk per MMA because the descriptors were computed inside the divergent
+// `if (elect_one_sync())` region: per-thread registers, i.e. an R2UR round trip for every operand of every MMA.  With
+// these forms ALL 32 lanes run the same (uniform) address arithmetic, control flow never diverges, and only the tensor-core
+// instruction itself is predicated on the lane elected once at kernel start.
+__device__ __forceinline__ void umma_bf16_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc,
+                                            uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(issue)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -244,45 +291,39 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
                       (p.khfold ? e * 3 : (int)p.taps.widx[e]) * p.Cout);
     }
     if (!p.a_cpasync) {
-      // ---- TMA: lane 0 of each of the 4 producer warps issues every 4th pipeline stage, so that the per-stage
-      // issue latency (barrier probe, coordinate math, descriptor fetch) of one thread does not pace the ring
-      if (lane == 0) {
-        const int np = 1;                           // producers in use (4 did not help: the consumer paces the ring)
-        if (warp < np) {
-          long long dbg_acc = 0; const long long dbg_t0 = p.dbg ? clock64() : 0;
-          int s = warp; uint32_t ph = 0;            // stage / phase of this producer's next iteration
-          int git = 0;                              // global iteration counter (all tiles, all k-iterations)
-          for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int cls = tile / tiles_per_cls;
-            int r = tile - cls * tiles_per_cls;
-            const int n = r / tiles_per_n;
-            r -= n * tiles_per_n;
-            const int tw = r % p.nTw; r /= p.nTw;
-            const int th = r % p.nTh;
-            const int td = r / p.nTh;
-            const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TWstep * p.in_scale;
-            const int e0 = p.taps.first[cls];
-            const int ntap = p.taps.first[cls + 1] - e0;
-            for (int t = 0; t < ntap; ++t) {
-              const int e = e0 + t;
-              const int cw = w0 + p.taps.dw[e], ch = h0 + p.taps.dh[e], cd = d0 + p.taps.dd[e];
-              const int wrow = (int)p.taps.widx[e] * p.Cout;
-              for (int kc = 0; kc < p.kchunks; ++kc, ++git) {
-                if ((git % np) != warp) continue;
-                const long long t0 = p.dbg ? clock64() : 0;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                if (p.dbg) dbg_acc += clock64() - t0;
-                mbar_expect_tx(full_bar(s), p.a_bytes + (p.b_resident ? 0u : p.b_bytes));
-                const uint32_t a_dst = ring_base + s * p.stage_bytes;
-                tma_load_5d(a_dst, &tmx, full_bar(s), kc * p.KC, cw, ch, cd, n);
-                if (!p.b_resident) tma_load_2d(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, wrow);
-                s += np;
-                if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
-              }
+      // ---- TMA: warp 0 walks the tile schedule with all lanes (uniform coordinates), one elected lane issues
+      if (warp == 0) {
+        const uint32_t issue = elect_one_sync() ? 1u : 0u;
+        long long dbg_acc = 0;
+        int s = 0; uint32_t ph = 0;               // stage / phase of the next iteration
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          const int cls = tile / tiles_per_cls;
+          int r = tile - cls * tiles_per_cls;
+          const int n = r / tiles_per_n;
+          r -= n * tiles_per_n;
+          const int tw = r % p.nTw; r /= p.nTw;
+          const int th = r % p.nTh;
+          const int td = r / p.nTh;
+          const int d0 = td * p.TD * p.in_scale, h0 = th * p.TH * p.in_scale, w0 = tw * p.TWstep * p.in_scale;
+          const int e0 = p.taps.first[cls];
+          const int ntap = p.taps.first[cls + 1] - e0;
+          for (int t = 0; t < ntap; ++t) {
+            const int e = e0 + t;
+            const int cw = w0 + p.taps.dw[e], ch = h0 + p.taps.dh[e], cd = d0 + p.taps.dd[e];
+            const int wrow = (int)p.taps.widx[e] * p.Cout;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              const long long t0 = p.dbg ? clock64() : 0;
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              if (p.dbg) dbg_acc += clock64() - t0;
+              mbar_expect_tx_p(full_bar(s), p.a_bytes + (p.b_resident ? 0u : p.b_bytes), issue);
+              const uint32_t a_dst = ring_base + s * p.stage_bytes;
+              tma_load_5d_p(a_dst, &tmx, full_bar(s), kc * p.KC, cw, ch, cd, n, issue);
+              if (!p.b_resident) tma_load_2d_p(a_dst + a_region, &tmw, full_bar(s), kc * p.KC, wrow, issue);
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
           }
-          if (p.dbg && warp == 0) { p.dbg[blockIdx.x * 8 + 0] = dbg_acc; }
         }
+        if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = dbg_acc; }
       }
     } else {
       // ---- cp.async gather: thread -> (16-byte chunk j of the row, rows rsub + i*rpp), written with the same
@@ -360,6 +401,7 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       int s = 0; uint32_t ph = 0;
       uint32_t a_addr = ring_base, fullb = full_bar(0), emptyb = empty_bar(0);
       int acc = 0; uint32_t accph = 0;
+      const uint32_t issue = elect_one_sync() ? 1u : 0u;     // the one lane whose tcgen05 instructions are not predicated off
       long long w_full = 0, w_tempty = 0, w_mma = 0, w_commit = 0; const long long mt0 = dbg ? clock64() : 0;
       if (bres) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gstride) {
@@ -375,6 +417,8 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * Nmma;
         uint32_t b_addr = bres_base + (uint32_t)(e0 * kchunks) * b_region;
+        uint32_t kh_b_addr = bres_base;     // kh-fold: resident weight tile (kd, kh = 0, kc) of the current stage
+        int kh_kc = 0;
         uint32_t accflag = 0;
         for (int it = 0; it < kiters; ++it) {
           if (dbg) t0 = clock64();
@@ -383,34 +427,34 @@ tc_conv_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
           if (cpa) fence_proxy_async();
           tc_fence_after();
           long long t1 = dbg ? clock64() : 0;
-          if (elect_one_sync()) {
           if (!khfold) {
             const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
             const uint64_t bdesc = desc_hi | (uint64_t)(((bres ? b_addr : a_addr + a_region) >> 4) & 0x3FFF);
 #pragma unroll 4
             for (int k = 0; k < ksteps; ++k) {  // +32 B per K=16 step inside the swizzled row (encoded >>4)
-              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accflag);
+              umma_bf16_p(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accflag, issue);
               accflag = 1;
             }
           } else {
-            // it = kd * kchunks + kc ; kh = 0,1,2 reads box lines kh .. kh+TH-1 (row offset kh * TW rows, a multiple
+            // stage = (kd, kc); kh = 0,1,2 reads box lines kh .. kh+TH-1 (row offset kh * TW rows, a multiple
             // of the 8-row swizzle atom) against the resident weight tile (kd, kh, kc)
-            const int kd = it / kchunks, kc = it - kd * kchunks;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
               const uint64_t adesc = desc_hi | (uint64_t)(((a_addr + (uint32_t)kh * line_bytes) >> 4) & 0x3FFF);
-              const uint32_t bt = bres_base + (uint32_t)(((kd * 3 + kh) * kchunks + kc)) * b_region;
+              const uint32_t bt = kh_b_addr + (uint32_t)(kh * kchunks) * b_region;
               const uint64_t bdesc = desc_hi | (uint64_t)((bt >> 4) & 0x3FFF);
 #pragma unroll 4
               for (int k = 0; k < ksteps; ++k) {
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accflag);
+                umma_bf16_p(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accflag, issue);
                 accflag = 1;
               }
             }
+            // next stage: kc + 1, or the next kd's first chunk (weight tiles are laid out [(kd*3+kh)*kchunks + kc])
+            if (++kh_kc == kchunks) { kh_kc = 0; kh_b_addr += (uint32_t)(2 * kchunks + 1) * b_region; }
+            else kh_b_addr += b_region;
           }
-          umma_commit(emptyb);
-          if (it == kiters - 1) umma_commit(tfull_bar(acc));
-          }
+          umma_commit_p(emptyb, issue);
+          if (it == kiters - 1) umma_commit_p(tfull_bar(acc), issue);
           __syncwarp();
           accflag = 1;
           long long t2 = dbg ? clock64() : 0;
@@ -560,8 +604,10 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
   const int tiles_per_n = p.nTd * p.nTh * p.nTw;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
+    {
+      // ===== TMA producer: all lanes walk the (uniform) schedule, one elected lane issues =====
+      const uint32_t issue = elect_one_sync() ? 1u : 0u;
+      const bool one_tap = p.ntaps == 1;
       int s = 0; uint32_t ph = 0;
       int bs = 0; uint32_t bph = 0;
       for (int c = c_begin; c < c_end; ++c) {
@@ -573,20 +619,25 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
         const int d0 = td * p.TD, h0 = th * p.TH, w0 = tw * p.TW;
         const int ad0 = d0 * p.a_scale - 1, ah0 = h0 * p.a_scale - 1, aw0 = w0 * p.a_scale - 1;
         mbar_wait(bempty(bs), bph ^ 1u);
-        mbar_expect_tx(bfull(bs), p.b_sub_bytes * p.nsub_b);
+        mbar_expect_tx_p(bfull(bs), p.b_sub_bytes * p.nsub_b, issue);
         for (int j = 0; j < p.nsub_b; ++j)
-          tma_load_5d(b_base + bs * p.b_stage_bytes + j * p.b_sub_bytes, &tmdy, bfull(bs), j * p.CWn, w0, h0, d0, n);
+          tma_load_5d_p(b_base + bs * p.b_stage_bytes + j * p.b_sub_bytes, &tmdy, bfull(bs), j * p.CWn, w0, h0, d0, n, issue);
         if (++bs == 2) { bs = 0; bph ^= 1u; }
+        // sub-tile u = g*SPG + j  ->  (tap, channel chunk), tracked incrementally (no per-load divisions)
+        int tap = (g_begin * p.SPG) / p.sub_per_tap, sub = (g_begin * p.SPG) - tap * p.sub_per_tap;
+        int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
         for (int g = g_begin; g < g_end; ++g) {
           const int u0 = g * p.SPG;
           const int nsub = min(p.SPG, p.total_sub - u0);
           mbar_wait(aempty(s), ph ^ 1u);
-          mbar_expect_tx(afull(s), p.a_sub_bytes * nsub);
+          mbar_expect_tx_p(afull(s), p.a_sub_bytes * nsub, issue);
           for (int j = 0; j < nsub; ++j) {
-            const int u = u0 + j;
-            const int tap = u / p.sub_per_tap, ch0 = (u - tap * p.sub_per_tap) * p.CW;
-            const int kd = p.ntaps == 1 ? 1 : tap / 9, kh = p.ntaps == 1 ? 1 : (tap / 3) % 3, kw = p.ntaps == 1 ? 1 : tap % 3;
-            tma_load_5d(smem_base + s * p.a_stage_bytes + j * p.a_sub_bytes, &tmx, afull(s), ch0, aw0 + kw, ah0 + kh, ad0 + kd, n);
+            tma_load_5d_p(smem_base + s * p.a_stage_bytes + j * p.a_sub_bytes, &tmx, afull(s), sub * p.CW,
+                          aw0 + (one_tap ? 1 : kw), ah0 + (one_tap ? 1 : kh), ad0 + (one_tap ? 1 : kd), n, issue);
+            if (++sub == p.sub_per_tap) {
+              sub = 0;
+              if (++kw == 3) { kw = 0; if (++kh == 3) { kh = 0; ++kd; } }
+            }
           }
           if (++s == p.a_stages) { s = 0; ph ^= 1u; }
         }
@@ -603,30 +654,32 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       const uint64_t adesc_hi = umma_desc(0, p.a_sub_bytes, p.a_sbo, p.a_layout);
       const uint64_t bdesc_hi = umma_desc(0, p.b_sub_bytes, p.b_sbo, p.b_layout);
       const uint64_t a_adv = (uint64_t)((2u * p.a_sbo) >> 4), b_adv = (uint64_t)((2u * p.b_sbo) >> 4);
+      const uint32_t issue = elect_one_sync() ? 1u : 0u;
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(bfull(bs), bph);
         tc_fence_after();
         const uint64_t bdesc = bdesc_hi | (uint64_t)(((b_base + bs * b_stage_bytes) >> 4) & 0x3FFF);
+        const uint32_t accflag0 = (c != c_begin) ? 1u : 0u;
+        uint32_t d_tmem = tmem_base;
         for (int g = g_begin; g < g_end; ++g) {
           mbar_wait(afull(s), ph);
           tc_fence_after();
-          if (elect_one_sync()) {
-            const uint64_t adesc = adesc_hi | (uint64_t)(((smem_base + s * a_stage_bytes) >> 4) & 0x3FFF);
-            const uint32_t d_tmem = tmem_base + (uint32_t)((g - g_begin) * Cout);
+          const uint64_t adesc = adesc_hi | (uint64_t)(((smem_base + s * a_stage_bytes) >> 4) & 0x3FFF);
+          uint64_t ad = adesc, bd = bdesc;
+          umma_bf16_p(d_tmem, ad, bd, idesc, accflag0, issue);
 #pragma unroll 4
-            for (int k = 0; k < ksteps; ++k)   // advance 16 voxel rows = 2 swizzle-atom groups = 2*SBO bytes
-              umma_bf16(d_tmem, adesc + a_adv * k, bdesc + b_adv * k, idesc, (c != c_begin) || (k != 0));
-            umma_commit(aempty(s));
+          for (int k = 1; k < ksteps; ++k) {   // advance 16 voxel rows = 2 swizzle-atom groups = 2*SBO bytes
+            ad += a_adv; bd += b_adv;
+            umma_bf16_p(d_tmem, ad, bd, idesc, 1u, issue);
           }
-          __syncwarp();
+          umma_commit_p(aempty(s), issue);
+          d_tmem += (uint32_t)Cout;
           if (++s == a_stages) { s = 0; ph ^= 1u; }
         }
-        if (elect_one_sync()) umma_commit(bempty(bs));
-        __syncwarp();
+        umma_commit_p(bempty(bs), issue);
         if (++bs == 2) { bs = 0; bph ^= 1u; }
       }
-      if (elect_one_sync()) umma_commit(accfull);
-      __syncwarp();
+      umma_commit_p(accfull, issue);
     }
   } else if (warp >= 4) {
     // ===== epilogue: accumulators -> fp32 partials =====
@@ -1074,6 +1127,8 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
     hdf_set_error("hdf_tc_conv3d_fwd: unsupported channels Cin=%d Cout=%d", Cin, Cout);
     return HDF_ERR_UNSUPPORTED;
   }
+  if (hdf_tc_ws_supported(mode, Cin, Cout))
+    return hdf_tc_ws_conv3d_fwd(x, ldx, w_packed_bf16, bias, y, ldy, N, Do, Ho, Wo, Cin, stream);
   return tc_conv_fwd_launch(mode, x, ldx, w_packed_bf16, bias, y, ldy, N, Do, Ho, Wo, Cin, Cout, stream);
 }
 

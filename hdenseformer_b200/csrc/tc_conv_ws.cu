@@ -3,9 +3,10 @@
 // model's FLOPs.
 //
 // Why a second formulation.  tc_conv_fwd_kernel (tc_conv.cu) puts the voxels on the MMA's M side (A operand = input box in
-// shared memory) and Cout (x3 kw taps) on N.  Measured on B200 (profiles/r1_umma_probe.txt): an SS-mode M=128 tcgen05.mma
-// costs >= 130 clk with 64-byte operand rows whatever N is, so N = 96 runs the tensor pipe at ~37 % at best.  Here the roles
-// are swapped and the weights never leave the tensor core's own memory:
+// shared memory) and Cout (x3 kw taps) on N = 96.  Measured on B200 (profiles/r2_umma_probe2.txt): an SS-mode MMA is bound
+// by the 128 B/clk the tensor core reads from shared memory -- (4 KB of A + 32 N bytes of B) / 128 clk, i.e. 56 clk for
+// N = 96 against 48 clk of math -- and that shared memory is also where TMA writes the next boxes (3 per tile).  Here the
+// roles are swapped and the weights never leave the tensor core's own memory:
 //     D[(kw, co), v] += sum_ci  Wt[kd,kh,kw][co][ci] * X[v + (kd,kh)][ci]
 //   * A operand = weights, M = 128 rows = 3 kw taps x 32 output channels (+32 zero rows), bf16 pairs resident in TMEM
 //     for the whole kernel (written once with tcgen05.st); TS-mode MMAs read no A bytes from shared memory, so an MMA
@@ -122,16 +123,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
   if (warp == 0) {
     // ===== TMA producer: one box per input plane z = d0-1 .. d1 of every work item (planes outside the volume are
     // zero-filled by TMA = the convolution's padding along D; same for the h / w halo)
-    if (lane == 0) {
-      uint32_t pp = 0;
+    {
+      const uint32_t issue = elect_one_sync() ? 1u : 0u;
+      uint32_t s = 0, ph = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         int n, d0, d1, h0, w0;
         decode(item, n, d0, d1, h0, w0);
-        for (int z = d0 - 1; z <= d1; ++z, ++pp) {
-          const uint32_t s = pp % (uint32_t)S, ph = (pp / (uint32_t)S) & 1u;
+        for (int z = d0 - 1; z <= d1; ++z) {
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), p.box_bytes);
-          tma_load_5d(ring_base + s * p.stage_bytes, &tmx, full_bar(s), 0, w0 - 1, h0 - 1, z, n);
+          mbar_expect_tx_p(full_bar(s), p.box_bytes, issue);
+          tma_load_5d_p(ring_base + s * p.stage_bytes, &tmx, full_bar(s), 0, w0 - 1, h0 - 1, z, n, issue);
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -142,8 +144,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
     const int ksteps = p.ksteps;
     const uint32_t stage_bytes = p.stage_bytes, line_bytes = p.line_bytes;
     const uint32_t w_tmem = tmem_base + p.w_col0;
-    uint32_t cp = 0;       // ring position of plane d0-1 of the current item
-    uint32_t waited = 0;   // ring positions [0, waited) have been observed full
+    const uint32_t issue = elect_one_sync() ? 1u : 0u;
+    // ring bookkeeping, all incremental (no divisions on the issue path): s0 = slot of plane d-1 of the current tile;
+    // (ws, wph) = next slot / phase to be observed full; ahead = planes observed full from s0 on (need 3 per tile)
+    uint32_t s0 = 0, ws = 0, wph = 0;
+    int ahead = 0;
     int acc = 0; uint32_t accph = 0;
     long long w_full = 0, w_tempty = 0; const long long mt0 = p.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -152,42 +157,45 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
       const int nd = d1 - d0;
       for (int t = 0; t < nd; ++t) {
         long long t0 = p.dbg ? clock64() : 0;
-        while (waited <= cp + (uint32_t)t + 2u) {
-          mbar_wait(full_bar(waited % (uint32_t)S), (waited / (uint32_t)S) & 1u);
-          ++waited;
+        while (ahead < 3) {
+          mbar_wait(full_bar(ws), wph);
+          if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; }
+          ++ahead;
         }
         if (p.dbg) { const long long t1 = clock64(); w_full += t1 - t0; t0 = t1; }
         mbar_wait(tempty_bar(acc), accph ^ 1u);
         if (p.dbg) w_tempty += clock64() - t0;
         tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t d_tmem = tmem_base + p.acc_col0 + (uint32_t)acc * p.acc_stride;
-          uint32_t accflag = 0;
+        const uint32_t d_tmem = tmem_base + p.acc_col0 + (uint32_t)acc * p.acc_stride;
+        const uint32_t s1 = s0 + 1 == (uint32_t)S ? 0u : s0 + 1;
+        const uint32_t s2 = s1 + 1 == (uint32_t)S ? 0u : s1 + 1;
+        uint32_t accflag = 0;
 #pragma unroll
-          for (int kd = 0; kd < 3; ++kd) {
-            const uint32_t slot = (cp + (uint32_t)t + (uint32_t)kd) % (uint32_t)S;
-            const uint32_t box = ring_base + slot * stage_bytes;
+        for (int kd = 0; kd < 3; ++kd) {
+          const uint32_t box = ring_base + (kd == 0 ? s0 : kd == 1 ? s1 : s2) * stage_bytes;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              const uint64_t bdesc = desc_hi | (uint64_t)(((box + (uint32_t)kh * line_bytes) >> 4) & 0x3FFF);
-              const uint32_t a0 = w_tmem + (uint32_t)((kd * 3 + kh) * ksteps * 8);
-              for (int ks = 0; ks < ksteps; ++ks) {     // +32 B per K=16 step inside the swizzled row (encoded >>4)
-                umma_ts(d_tmem, a0 + (uint32_t)(ks * 8), bdesc + (uint64_t)(2 * ks), idesc, accflag);
-                accflag = 1;
-              }
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint64_t bdesc = desc_hi | (uint64_t)(((box + (uint32_t)kh * line_bytes) >> 4) & 0x3FFF);
+            const uint32_t a0 = w_tmem + (uint32_t)((kd * 3 + kh) * ksteps * 8);
+            for (int ks = 0; ks < ksteps; ++ks) {     // +32 B per K=16 step inside the swizzled row (encoded >>4)
+              umma_ts_p(d_tmem, a0 + (uint32_t)(ks * 8), bdesc + (uint64_t)(2 * ks), idesc, accflag, issue);
+              accflag = 1;
             }
           }
-          umma_commit(empty_bar((cp + (uint32_t)t) % (uint32_t)S));          // plane d-1 is no longer needed
-          if (t == nd - 1) {                                                  // end of the column: release the last two planes
-            umma_commit(empty_bar((cp + (uint32_t)t + 1u) % (uint32_t)S));
-            umma_commit(empty_bar((cp + (uint32_t)t + 2u) % (uint32_t)S));
-          }
-          umma_commit(tfull_bar(acc));
         }
-        __syncwarp();
+        umma_commit_p(empty_bar(s0), issue);             // plane d-1 is no longer needed
+        if (t == nd - 1) {                               // end of the column: release the last two planes as well
+          umma_commit_p(empty_bar(s1), issue);
+          umma_commit_p(empty_bar(s2), issue);
+          s0 = s2 + 1 == (uint32_t)S ? 0u : s2 + 1;
+          ahead -= 3;
+        } else {
+          s0 = s1;
+          ahead -= 1;
+        }
+        umma_commit_p(tfull_bar(acc), issue);
         if (++acc == 2) { acc = 0; accph ^= 1u; }
       }
-      cp += (uint32_t)nd + 2u;
     }
     if (p.dbg && lane == 0) {
       p.dbg[blockIdx.x * 8 + 0] = (unsigned long long)w_full; p.dbg[blockIdx.x * 8 + 1] = (unsigned long long)w_tempty;
@@ -286,10 +294,12 @@ EncodeTiledFn ws_get_encode() {
 
 }  // namespace
 
+extern "C" {
+
 // 1 if the weight-stationary kernel takes this stride-1 convolution
 int hdf_tc_ws_supported(int mode, int Cin, int Cout) {
-  static const char* off = getenv("HDF_TC_NO_WS");
-  return !off && mode == 0 && Cout == WS_COUT && (Cin == 32 || Cin == 64);
+  const char* off = getenv("HDF_TC_NO_WS");     // read per call: tests and benches A/B the two kernels in one process
+  return !(off && off[0] == '1') && mode == 0 && Cout == WS_COUT && (Cin == 32 || Cin == 64);
 }
 
 // Plan + launch.  Same contract as hdf_tc_conv3d_fwd(mode 0): x [N,D,H,W,Cin] bf16 (channel stride ldx), packed weights
@@ -402,3 +412,5 @@ int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16
   }
   return HDF_OK;
 }
+
+}  // extern "C"

@@ -104,6 +104,20 @@ def tc_conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
+def tc_ws_supported(mode: int, Cin: int, Cout: int) -> bool:
+    return bool(_lib().hdf_tc_ws_supported(mode, Cin, Cout))
+
+
+def tc_ws_conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor):
+    """weight-stationary kernel (Cout = 32, Cin in {32, 64}); same operands as tc_conv3d_fwd(mode 0)"""
+    N, D, H, W, Cout = out.shape
+    Cin = x.shape[-1]
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and Cout == 32
+    _C.check(_lib().hdf_tc_ws_conv3d_fwd(_p(x), _ld(x), _p(wp), _p(bias), _p(out), _ld(out), N, D, H, W, Cin, _s()),
+             "tc_ws_conv3d_fwd")
+    return out
+
+
 def tc_wgrad_supported(mode: int, Cin: int, Cout: int) -> bool:
     return bool(_lib().hdf_tc_wgrad_supported(mode, Cin, Cout))
 

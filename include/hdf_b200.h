@@ -55,6 +55,12 @@ int hdf_tc_pack_weights(const float* w, void* packed_bf16, int Cin, int Cout, lo
                         channels ci >= cin_valid are zero (K padding for 2..4-channel inputs) */
 int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y,
                       long long ldy, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* stream);
+/* weight-stationary variant for Cout = 32, Cin in {32, 64}, stride 1 (csrc/tc_conv_ws.cu): weights resident in TMEM as
+ * the A operand, voxels on the MMA's N side, one TMA box per input plane shared by three output planes.  hdf_tc_conv3d_fwd
+ * dispatches to it (HDF_TC_NO_WS=1 disables); exported so that tests can compare both kernels on the same operands. */
+int hdf_tc_ws_supported(int mode, int Cin, int Cout);
+int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
+                         int N, int D, int H, int W, int Cin, void* stream);
 int hdf_tc_wgrad_supported(int mode, int Cin, int Cout);   /* mode 0 or 1 */
 size_t hdf_tc_wgrad_workspace(int mode, int N, int Do, int Ho, int Wo, int Cin, int Cout);
 int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,

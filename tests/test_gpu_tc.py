@@ -67,6 +67,65 @@ def test_tc_conv_fwd_matches_torch(cin, cout, size, N):
         assert err < 1e-2, err
 
 
+WS_CASES = [
+    # cin, (D,H,W), N, bias
+    (32, (6, 8, 30), 1, False),        # one W tile exactly (30 output columns), partial H tiles
+    (32, (5, 13, 37), 2, True),        # ragged everything, 2 samples, bias (UpConv up3 has one)
+    (64, (7, 9, 64), 1, False),        # 128-byte rows, 3 W tiles
+    (64, (4, 20, 31), 2, True),
+    (32, (40, 16, 16), 1, False),      # long D column: several ring wrap-arounds and D segments
+    (32, (3, 3, 3), 1, True),          # volume smaller than one tile
+]
+
+
+@pytest.mark.parametrize("cin,size,N,use_bias", WS_CASES)
+def test_tc_ws_conv_matches_torch_and_old_kernel(cin, size, N, use_bias):
+    """Weight-stationary tcgen05 kernel (csrc/tc_conv_ws.cu: weights in TMEM, voxels on the MMA N side, plane ring) against
+    torch's fp32 conv on the bf16-rounded operands, and bit-for-bit-close to the first-generation kernel; forward and
+    input-gradient forms, channel-slice operands."""
+    import os
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    cout = 32
+    assert ops.tc_ws_supported(0, cin, cout)
+    torch.manual_seed(cin + size[2])
+    xb = torch.randn(N, *size, cin + 16, device=DEV).to(torch.bfloat16)
+    xs = xb[..., 8:8 + cin]
+    w = torch.randn(cout, cin, 3, 3, 3, device=DEV) / math.sqrt(27 * cin)
+    b = torch.randn(cout, device=DEV) if use_bias else None
+    wq = w.to(torch.bfloat16).float()
+    ref = F.conv3d(xs.float().permute(0, 4, 1, 2, 3), wq, b, padding=1).permute(0, 2, 3, 4, 1)
+    buf = torch.zeros(N, *size, cout + 32, dtype=torch.bfloat16, device=DEV)
+    y = buf[..., 32:]
+    wp = ops.tc_pack(w, cin, cout, 27, cin * 27, False)
+    ops.tc_ws_conv3d_fwd(xs, wp, b, y)
+    torch.cuda.synchronize()
+    err = ((y.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-2, err
+    assert buf[..., :32].abs().max().item() == 0
+    # same operands through the first-generation kernel (voxels on M): both round the same fp32 sums to bf16
+    os.environ["HDF_TC_NO_WS"] = "1"
+    try:
+        y_old = torch.empty(N, *size, cout, dtype=torch.bfloat16, device=DEV)
+        ops.tc_conv3d_fwd(xs, wp, b, y_old)
+    finally:
+        os.environ["HDF_TC_NO_WS"] = "0"
+    torch.cuda.synchronize()
+    d = (y.float() - y_old.float()).abs().max().item() / ref.abs().max().item()
+    assert d < 8e-3, d          # at most one bf16 ulp apart (different fp32 summation order)
+    # input-gradient form of a Cin'=cout... layer whose dgrad has 32 output channels: dy has `cin` channels, dx 32
+    g = torch.randn(N, *size, cin, device=DEV).to(torch.bfloat16)
+    w2 = torch.randn(cin, cout, 3, 3, 3, device=DEV) / math.sqrt(27 * cout)      # Conv3d(32 -> cin) weight
+    w2q = w2.to(torch.bfloat16).float()
+    xr = torch.zeros(N, cout, *size, device=DEV, requires_grad=True)
+    F.conv3d(xr, w2q, None, padding=1).backward(g.float().permute(0, 4, 1, 2, 3))
+    wpd = ops.tc_pack(w2, cin, cout, cout * 27, 27, True)       # packed[tap][n = ci(32)][k = co(cin)] = w2[co][ci][26 - tap]
+    dx = torch.empty(N, *size, cout, dtype=torch.bfloat16, device=DEV)
+    ops.tc_ws_conv3d_fwd(g, wpd, None, dx)
+    refdx = xr.grad.permute(0, 2, 3, 4, 1)
+    err = ((dx.float() - refdx).abs().max() / refdx.abs().max()).item()
+    assert err < 1e-2, err
+
+
 def test_tc_conv_matches_simt_path_large():
     """72^3 x 32->32: thousands of tiles through the persistent scheduler, vs our own SIMT kernel."""
     ops.ensure_init(torch.zeros(1, device=DEV))
