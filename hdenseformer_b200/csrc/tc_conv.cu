@@ -1519,6 +1519,7 @@ static bool wgrad_swap_roles(int mode, int Cin, int Cout) { return mode == 0 && 
 
 size_t hdf_tc_wgrad_workspace(int mode, int N, int Do, int Ho, int Wo, int Cin, int Cout) {
   if (!hdf_tc_wgrad_supported(mode, Cin, Cout)) return 0;
+  if (hdf_tc_wgrad_ws_supported(mode, Cin, Cout)) return hdf_tc_wgrad_ws_workspace(N, Do, Ho, Wo, Cin, Cout);
   if (!wgrad_use_v1()) {
     const Wg2Roles r = wg2_roles(mode, Cin, Cout);
     TcWgrad2Params q;
@@ -1543,6 +1544,8 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
   HDF_REQUIRE(x && dy && dw && workspace, "hdf_tc_conv3d_wgrad: null pointer");
   HDF_REQUIRE((ldx % 8 == 0) && (ldy % 8 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0),
               "hdf_tc_conv3d_wgrad: operands must be 16-byte aligned with channel strides multiple of 8");
+  if (hdf_tc_wgrad_ws_supported(mode, Cin, Cout))
+    return hdf_tc_wgrad_ws(x, ldx, dy, ldy, dw, stride_ci, stride_co, N, Do, Ho, Wo, Cin, Cout, workspace, ws_bytes, accumulate, stream);
   if (!wgrad_use_v1())
     return tc_wgrad2_launch(mode, x, ldx, dy, ldy, dw, stride_ci, stride_co, N, Do, Ho, Wo, Cin, Cout, workspace, ws_bytes,
                             accumulate, (cudaStream_t)stream);

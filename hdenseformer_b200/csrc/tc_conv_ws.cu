@@ -33,7 +33,7 @@ int hdf_sm_count_cached();
 namespace {
 using namespace tcptx;
 
-constexpr int WS_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int WS_THREADS = 320;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue (2 per TMEM lane quarter)
 constexpr int WS_COUT = 32;
 
 struct WsParams {
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
     const int q = warp & 3;
     const int kw = lane >> 3, c = lane & 7;
     const bool valid = lane < 24;
-    for (int b = 0; b < 9; ++b) {
+    for (int b = (warp - 2) >> 2; b < 9; b += 2) {
       const bf16* row = p.wp + ((size_t)((b * 3 + (valid ? kw : 0)) * WS_COUT + q * 8 + c)) * p.Cin;
       for (int ks = 0; ks < p.ksteps; ++ks) {
         uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
     uint32_t s0 = 0, ws = 0, wph = 0;
     int ahead = 0;
     int acc = 0; uint32_t accph = 0;
+    bool tempty_ok = false;    // the current tile's accumulator was already observed free (during the previous tile)
     long long w_full = 0, w_tempty = 0; const long long mt0 = p.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int n, d0, d1, h0, w0;
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
           ++ahead;
         }
         if (p.dbg) { const long long t1 = clock64(); w_full += t1 - t0; t0 = t1; }
-        mbar_wait(tempty_bar(acc), accph ^ 1u);
+        if (!tempty_ok) mbar_wait(tempty_bar(acc), accph ^ 1u);
+        tempty_ok = false;
         if (p.dbg) w_tempty += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + p.acc_col0 + (uint32_t)acc * p.acc_stride;
@@ -172,6 +174,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
         uint32_t accflag = 0;
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
+          if (kd == 2 && t + 1 < nd) {
+            // The barrier round trips of the NEXT tile (its newest plane, its accumulator) are taken here, while the
+            // tensor core still works through the MMAs queued above: the issuing thread runs in lockstep with the
+            // tensor pipe (MMA issue blocks when the queue is full), so waits at the tile boundary were pure bubbles.
+            long long t2 = p.dbg ? clock64() : 0;
+            mbar_wait(full_bar(ws), wph);
+            if (++ws == (uint32_t)S) { ws = 0; wph ^= 1u; }
+            ++ahead;
+            if (p.dbg) { const long long t3 = clock64(); w_full += t3 - t2; t2 = t3; }
+            mbar_wait(tempty_bar(acc ^ 1), (acc == 1 ? accph ^ 1u : accph) ^ 1u);
+            tempty_ok = true;
+            if (p.dbg) w_tempty += clock64() - t2;
+            tc_fence_after();
+          }
           const uint32_t box = ring_base + (kd == 0 ? s0 : kd == 1 ? s1 : s2) * stage_bytes;
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
@@ -202,13 +218,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
       p.dbg[blockIdx.x * 8 + 2] = (unsigned long long)(clock64() - mt0);
     }
   } else {
-    // ===== epilogue warps 2..5 (TMEM lane quarter q = warp % 4: output channels 8q .. 8q+7)
-    const int q = warp & 3;
+    // ===== epilogue warps 2..9: TMEM lane quarter q = warp % 4 (output channels 8q .. 8q+7), two warps per quarter that
+    // take alternate lines of the tile
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int c = lane >> 2, pcol = lane & 3;
     const int src1 = (lane & ~3) | ((pcol + 1) & 3), src2 = (lane & ~3) | ((pcol + 2) & 3);
-    const int etid = threadIdx.x - 64;            // 0..127
+    const int etid = threadIdx.x - 64;            // 0..255
     const float bias = p.bias ? p.bias[q * 8 + c] : 0.f;
-    const int TW = GROUPS * 4, TWu = TW - 2;
+    constexpr int TW = GROUPS * 4, TWu = TW - 2;
+    const int TH = p.TH;
+    // staging offset of this thread's (channel, column phase): [line][column][32 ch] bf16, the voxel's four 16-byte channel
+    // groups XOR-swizzled by (column >> 1) so that the 2-byte stores of a warp spread over all banks
+    const uint32_t stg_thr = (uint32_t)(pcol * 64 + c * 2);
+    const int xs = pcol >> 1;
     int acc = 0; uint32_t accph = 0;
     long long e_wait = 0; const long long et0 = p.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -221,8 +243,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
         tc_fence_after();
         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + p.acc_col0 + (uint32_t)acc * p.acc_stride;
         uint8_t* stg = smem_gen + (stg_base - smem_base) + (uint32_t)acc * p.stg_bytes;
-        for (int lh = 0; lh < p.TH; ++lh) {
-          uint32_t a[2 * GROUPS], b[2 * GROUPS];
+        auto load_line = [&](int lh, uint32_t* a, uint32_t* b) {
           if (GROUPS == 8) {
             tmem_ld_16x128b_x8(tcol + (uint32_t)(lh * TW), a);
             tmem_ld_16x128b_x8(tcol + (16u << 16) + (uint32_t)(lh * TW), b);
@@ -230,7 +251,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
             tmem_ld_16x128b_x4(tcol + (uint32_t)(lh * TW), a);
             tmem_ld_16x128b_x4(tcol + (16u << 16) + (uint32_t)(lh * TW), b);
           }
-          tmem_ld_wait();
+        };
+        auto combine_line = [&](int lh, const uint32_t* a, const uint32_t* b) {
+          uint8_t* row = stg + (uint32_t)(lh * TW * 64) + stg_thr;
 #pragma unroll
           for (int g = 0; g < GROUPS; ++g) {
             const int gn = g + 1 < GROUPS ? g + 1 : g;
@@ -240,19 +263,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
             const float r1 = __shfl_sync(0xffffffffu, send1, src1);     // D1 at column j + 1
             const float r2 = __shfl_sync(0xffffffffu, send2, src2);     // D2 at column j + 2
             const float yv = __uint_as_float(a[2 * g]) + r1 + r2 + bias;
-            const int j = 4 * g + pcol;
-            // staging: [line][column][32 ch] bf16, the voxel's four 16-byte channel groups XOR-swizzled by (j >> 1)
-            *reinterpret_cast<bf16*>(stg + (uint32_t)((lh * TW + j) * 64) + (uint32_t)(((q ^ ((j >> 1) & 3)) * 16) + c * 2)) =
-                __float2bfloat16_rn(yv);
+            *reinterpret_cast<bf16*>(row + (uint32_t)(g * 256) + (uint32_t)((q ^ ((2 * g + xs) & 3)) * 16)) = __float2bfloat16_rn(yv);
+          }
+        };
+        {
+          uint32_t a0[2 * GROUPS], b0[2 * GROUPS], a1[2 * GROUPS], b1[2 * GROUPS];
+          int lh = half;
+          if (lh < TH) load_line(lh, a0, b0);
+          while (lh < TH) {
+            tmem_ld_wait();
+            if (lh + 2 < TH) load_line(lh + 2, a1, b1);
+            combine_line(lh, a0, b0);
+            lh += 2;
+            if (lh >= TH) break;
+            tmem_ld_wait();
+            if (lh + 2 < TH) load_line(lh + 2, a0, b0);
+            combine_line(lh, a1, b1);
+            lh += 2;
           }
         }
         // accumulator drained: hand it back to the MMA warp before the copy-out
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
-        named_bar_sync(1, 128);          // all four quarters of the tile are staged
-        const int nchunks = p.TH * TW * 4;
-        for (int idx = etid; idx < nchunks; idx += 128) {
+        named_bar_sync(1, 256);          // all four quarters of every line of the tile are staged
+        const int nchunks = TH * TW * 4;
+        for (int idx = etid; idx < nchunks; idx += 256) {
           const int voxel = idx >> 2, chunk = idx & 3;
           const int lh = voxel / TW, j = voxel - lh * TW;
           const int h = h0 + lh, w = w0 + j;

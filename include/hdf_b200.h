@@ -62,6 +62,14 @@ int hdf_tc_ws_supported(int mode, int Cin, int Cout);
 int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
                          int N, int D, int H, int W, int Cin, void* stream);
 int hdf_tc_wgrad_supported(int mode, int Cin, int Cout);   /* mode 0 or 1 */
+/* plane-ring weight gradient for stride-1 convs with a 32-channel operand (csrc/tc_wgrad_ws.cu): three w-shifted boxes of
+ * the 32-channel operand stacked along M, three line-shifted sub-tiles of the other operand stacked along N, its planes in a
+ * ring shared by three tiles.  hdf_tc_conv3d_wgrad dispatches to it (HDF_TC_NO_WGRAD_WS=1 disables). */
+int hdf_tc_wgrad_ws_supported(int mode, int Cin, int Cout);
+size_t hdf_tc_wgrad_ws_workspace(int N, int D, int H, int W, int Cin, int Cout);
+int hdf_tc_wgrad_ws(const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
+                    long long stride_co, int N, int D, int H, int W, int Cin, int Cout, void* workspace, size_t ws_bytes,
+                    int accumulate, void* stream);
 size_t hdf_tc_wgrad_workspace(int mode, int N, int Do, int Ho, int Wo, int Cin, int Cout);
 int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, long long ldy, float* dw, long long stride_ci,
                         long long stride_co, int N, int Do, int Ho, int Wo, int Cin, int Cout, void* workspace,

@@ -153,6 +153,13 @@ WG_CASES = [
     (256, 256, (9, 9, 9), 2),     # block_4_2_left / deep_conv at nf=32
     (256, 256, (18, 18, 18), 1),
     (512, 256, (9, 9, 9), 1),     # deep_conv with 4 modalities
+    # plane-ring kernel (csrc/tc_wgrad_ws.cu: one operand has 32 channels)
+    (32, 32, (20, 18, 50), 2),    # ragged H / W tiles, 2 samples
+    (32, 32, (40, 8, 16), 1),     # long D column: ring wrap-arounds, several D segments
+    (128, 32, (6, 10, 24), 1),    # P = dy, Q = x in 4 channel passes
+    (32, 256, (4, 9, 17), 1),     # P = x, Q = dy in 8 channel passes, W not a multiple of 8
+    (64, 32, (12, 12, 40), 2),    # block_1_1_right / up3 shape class
+    (32, 32, (3, 3, 3), 1),       # volume smaller than one tile
 ]
 
 
