@@ -98,6 +98,9 @@ class Engine:
         # fused layer-head kernels (Linear_l + LN1 + to_qkv): measured slower than the three single-op launches on B200
         # (34.2 vs 33.1 ms/step), so they stay opt-in
         self.fused_dct_head = os.environ.get("HDF_DCT_HEAD") == "1"
+        # bf16 path: tensor-core token kernels (mma.sync Linears / attention) instead of the fp32 SIMT ones
+        self.tok_tc = os.environ.get("HDF_NO_TOK_TC") is None
+        self._tok_bf16 = False
         self.use_side_stream = os.environ.get("HDF_NO_SIDE_STREAM") is None
         self._side = {}
         self._keep_alive = None
@@ -115,42 +118,62 @@ class Engine:
 
     # ------------------------------------------------------------------ conv helpers
     def _pack(self, w, Cin, Cout, sci, sco, flip, cin_valid=None):
-        """bf16 [27][Cout][Cin] operand tiles of a conv weight; taken from the per-step cache when `_prepack` filled it."""
+        """bf16 [27][Cout][Cin] operand tiles of a conv weight; taken from the per-step cache when `_prepack` filled it
+        (the consumer's stream then waits for THAT weight's event, not for the whole pre-pack pass)."""
         key = (w.data_ptr(), Cin, Cout, sci, sco, bool(flip), cin_valid)
-        t = self._packed.get(key)
-        if t is None:
-            t = ops.tc_pack(w, Cin, Cout, sci, sco, flip, cin_valid=cin_valid)
-            if self._packed_open:
-                self._packed[key] = t
+        hit = self._packed.get(key)
+        if hit is not None:
+            t, ev = hit
+            if ev is not None:
+                torch.cuda.current_stream(w.device).wait_event(ev)
+            return t
+        t = ops.tc_pack(w, Cin, Cout, sci, sco, flip, cin_valid=cin_valid)
+        if self._packed_open:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(w.device))
+            self._packed[key] = (t, ev)
         return t
 
+    _FWD_USE_ORDER = ("block_1_1_left", "block_1_2_left", "deep_conv", "up1", "up2", "up3", "block_2_1_left", "block_2_2_left",
+                      "block_3_1_left", "block_3_2_left", "block_4_1_left", "block_4_2_left", "upconv_3", "block_3_1_right",
+                      "block_3_2_right", "upconv_2", "block_2_1_right", "block_2_2_right", "upconv_1", "block_1_1_right",
+                      "block_1_2_right")
+
     def _prepack(self, P, dev, main_stream, need_dgrad):
-        """Pack every tensor-core conv weight of the step (forward and input-gradient layouts) on a side stream at the
-        start of the forward pass: ~40 small kernels leave the main stream's dependency chain (each sat right in front
-        of its convolution).  Returns the event the consumers wait on."""
+        """Pack every tensor-core conv weight of the step on a side stream at the start of the forward pass: ~40 small
+        kernels leave the main stream's dependency chain (each sat right in front of its convolution).  Weights are packed
+        in the order the step uses them (forward layouts in forward order, then the input-gradient layouts in backward
+        order) and every one gets its own event, so the first convolutions do not wait for the 2 x 22 MB of the deep layers
+        (profiles/r2_timeline_v3.txt: the single end-of-pass event gated the first encoder conv until 1.1 ms)."""
         st = self._side_stream(dev, 99, "p")
         st.wait_stream(main_stream)      # also orders the re-use of last step's buffers behind last step's kernels
         self._packed = {}
         self._packed_open = True
+        convs = [(k, w) for k, w in P.items() if w.dim() == 5 and w.shape[2:] == (3, 3, 3)]
+        rank = {n: i for i, n in enumerate(self._FWD_USE_ORDER)}
+        convs.sort(key=lambda kw: rank.get(kw[0].split(".")[0], len(rank)))
         with torch.cuda.stream(st):
-            for k, w in P.items():
-                if w.dim() != 5 or w.shape[2:] != (3, 3, 3):
-                    continue
+            for k, w in convs:                        # forward layouts
                 if k.startswith("upconv_"):          # ConvTranspose3d weight [Cin, Cout, 27]
                     Cin, Cout = w.shape[0], w.shape[1]
                     if ops.tc_supported(1, Cin, Cout):
                         self._pack(w, Cin, Cout, Cout * 27, 27, False)
-                    if need_dgrad and ops.tc_supported(2, Cout, Cin):
-                        self._pack(w, Cout, Cin, 27, Cout * 27, False)
                 else:                                 # Conv3d weight [Cout, Cin, 27]
                     Cout, Cin = w.shape[0], w.shape[1]
                     if ops.tc_supported(0, Cin, Cout):
                         self._pack(w, Cin, Cout, 27, Cin * 27, False, cin_valid=Cin)
-                    if need_dgrad and ops.tc_supported(0, Cout, Cin):
-                        self._pack(w, Cout, Cin, Cin * 27, 27, True)
-            ev = torch.cuda.Event()
-            ev.record(st)
-        return ev
+            if need_dgrad:
+                for k, w in reversed(convs):          # input-gradient layouts, in the order backward needs them
+                    if k.startswith("upconv_"):
+                        Cin, Cout = w.shape[0], w.shape[1]
+                        if ops.tc_supported(2, Cout, Cin):
+                            self._pack(w, Cout, Cin, 27, Cout * 27, False)
+                    else:
+                        Cout, Cin = w.shape[0], w.shape[1]
+                        if ops.tc_supported(0, Cout, Cin):
+                            self._pack(w, Cout, Cin, Cin * 27, 27, True)
+        self._packed_open = False
+        return None
 
     def _conv_fwd(self, x, w, bias, out, mode=0):
         """x: [N,D,H,W,Cin] view; w: torch-layout weight; out: [N,Do,Ho,Wo,Cout] view."""
@@ -258,6 +281,14 @@ class Engine:
         for l in range(4):
             q = f"{pre}layers.{l}."
             Cl = E + GROWTH * l
+            if self.tok_tc and self._tok_bf16:
+                # bf16 path: the whole inner layer in two tensor-core kernels (csrc/tok_tc.cu)
+                h0, n1, m1, r1, qkv = ops.tok_a_fwd(F, Cl, P, q)
+                ida, idb, idc, idd, ide = ids(), ids(), ids(), ids(), ids()
+                o, lse, sv = ops.tok_c_fwd(qkv, h0, P, q, F[:, Cl:Cl + GROWTH], B, R // B, (GROWTH // HEADS) ** -0.5, p, seed,
+                                           (ida, idb, idc, idd, ide))
+                layers.append(dict(h0=h0, n1=n1, m1=m1, r1=r1, qkv=qkv, o=o, lse=lse, sv=sv, ids=(ida, idb, idc, idd, ide)))
+                continue
             if self.fused_dct_head:
                 h0, n1, m1, r1, qkv = ops.dct_a_fwd(F, Cl, P, q)
             else:
@@ -391,6 +422,7 @@ class Engine:
         dev = x.device
         c = Ctx()
         c.x, c.dtype, c.training, c.seed, c.B = x, dtype, training, seed, B
+        self._tok_bf16 = dtype == torch.bfloat16
         counter = [0]
 
         def ids():
@@ -475,8 +507,6 @@ class Engine:
             up = empty((B, 2 * a.shape[1], 2 * a.shape[2], 2 * a.shape[3], a.shape[4]))
             return ops.upsample2_fwd(a, up)
 
-        if pack_ev is not None:
-            torch.cuda.current_stream(dev).wait_event(pack_ev)
         attnout = upconv("deep_conv", attnall)
         at1 = upconv("up1", attnout)
         at2 = upconv("up2", at1)
@@ -494,8 +524,6 @@ class Engine:
         # GEMMs have the GPU to themselves instead of queueing behind the 41 k blocks of the first encoder kernels.
         for ev in pe_events:
             main_stream.wait_event(ev)
-        if pack_ev is not None:
-            main_stream.wait_event(pack_ev)
         if self.use_tc and self.use_stem and dtype == torch.bfloat16 and ops.stem_supported(M, nf):
             xcl = ops.stem_im2col(x)        # first conv = one GEMM over the gathered taps (csrc/tc_conv.cu, stem path)
         else:

@@ -347,6 +347,43 @@ def dct_a_fwd(F, Cl, P, q):
     return h0, n1, m1, r1, qkv
 
 
+def tok_a_fwd(F, Cl, P, q):
+    """tensor-core (bf16 path) version of dct_a_fwd: same operands, same saved tensors (csrc/tok_tc.cu)"""
+    R = F.shape[0]
+    dev, f32 = F.device, torch.float32
+    h0 = torch.empty((R, 32), dtype=f32, device=dev)
+    n1 = torch.empty((R, 32), dtype=f32, device=dev)
+    m1 = torch.empty((R,), dtype=f32, device=dev)
+    r1 = torch.empty((R,), dtype=f32, device=dev)
+    qkv = torch.empty((R, 96), dtype=f32, device=dev)
+    _C.check(_lib().hdf_tok_a_fwd(_p(F), F.stride(0), Cl, _p(P[q + "0.weight"]), _p(P[q + "0.bias"]), _p(P[q + "1.norm.weight"]),
+                                  _p(P[q + "1.norm.bias"]), _p(P[q + "1.fn.to_qkv.weight"]), _p(h0), _p(n1), _p(m1), _p(r1),
+                                  _p(qkv), R, _s()), "tok_a_fwd")
+    return h0, n1, m1, r1, qkv
+
+
+def tok_c_fwd(qkv, h0, P, q, fout, B, N, scale, p, seed, ids):
+    """tensor-core attention (8 heads x 4) fused with the post-attention chain of dct_c_fwd.  Returns (o, lse, saved)."""
+    R = qkv.shape[0]
+    dev, f32 = qkv.device, torch.float32
+    o = torch.empty((R, 32), dtype=f32, device=dev)
+    lse = torch.empty((B, 8, N), dtype=f32, device=dev)
+    sv = dict(h1=torch.empty((R, 32), dtype=f32, device=dev), n2=torch.empty((R, 32), dtype=f32, device=dev),
+              z1=torch.empty((R, 64), dtype=f32, device=dev), f1=torch.empty((R, 64), dtype=f32, device=dev),
+              h2=torch.empty((R, 32), dtype=f32, device=dev), n3=torch.empty((R, 32), dtype=f32, device=dev),
+              z1b=torch.empty((R, 64), dtype=f32, device=dev), g1=torch.empty((R, 64), dtype=f32, device=dev),
+              m2=torch.empty((R,), dtype=f32, device=dev), r2=torch.empty((R,), dtype=f32, device=dev),
+              m3=torch.empty((R,), dtype=f32, device=dev), r3=torch.empty((R,), dtype=f32, device=dev))
+    sp, so = _seed_args(seed)
+    _C.check(_lib().hdf_tok_c_fwd(_p(qkv), _p(h0), _p(o), _p(lse), _p(sv["h1"]), _p(sv["n2"]), _p(sv["z1"]), _p(sv["f1"]), _p(sv["h2"]),
+                                  _p(sv["n3"]), _p(sv["z1b"]), _p(sv["g1"]), _p(sv["m2"]), _p(sv["r2"]), _p(sv["m3"]), _p(sv["r3"]),
+                                  _p(fout), fout.stride(0), _p(P[q + "1.fn.to_out.0.weight"]), _p(P[q + "1.fn.to_out.0.bias"]),
+                                  _p(P[q + "2.norm.weight"]), _p(P[q + "2.norm.bias"]), _p(P[q + "2.fn.net.0.weight"]),
+                                  _p(P[q + "2.fn.net.0.bias"]), _p(P[q + "2.fn.net.3.weight"]), _p(P[q + "2.fn.net.3.bias"]), B, N,
+                                  float(scale), float(p), sp, so, *ids, _s()), "tok_c_fwd")
+    return o, lse, sv
+
+
 def dct_a_bwd(dqkv, dh1, s, F, Cl, dF, P, G, q):
     """fused backward of dct_a_fwd: dF[:, :Cl] += ..., parameter gradients += into G."""
     R = F.shape[0]

@@ -140,6 +140,16 @@ int hdf_dct_c_fwd(const float* o, const float* h0, float* h1, float* n2, float* 
                   unsigned idb, unsigned idc, unsigned idd, unsigned ide, void* stream);
 int hdf_dct_a_fwd(const float* F, long long ldf, int Cl, const float* Wl, const float* bl, const float* gm, const float* bt,
                   const float* Wqkv, float* h0, float* n1, float* m1, float* r1, float* qkv, int R, void* stream);
+/* bf16-path tensor-core forward of the same layer (csrc/tok_tc.cu): mma.sync bf16 Linears, tf32 m16n8k4 / m16n8k8 for
+ * Q K^T / P V (head_dim 4 = the tf32 K atom), fp32 softmax statistics through warp shuffles.  hdf_tok_a_fwd has the operands
+ * of hdf_dct_a_fwd; hdf_tok_c_fwd = attention (writes o, lse [B,8,N]) + the chain of hdf_dct_c_fwd, same saved tensors. */
+int hdf_tok_a_fwd(const float* F, long long ldf, int Cl, const float* Wl, const float* bl, const float* gm, const float* bt,
+                  const float* Wqkv, float* h0, float* n1, float* m1, float* r1, float* qkv, int R, void* stream);
+int hdf_tok_c_fwd(const float* qkv, const float* h0, float* o, float* lse, float* h1, float* n2, float* z1, float* f1, float* h2,
+                  float* n3, float* z1b, float* g1, float* m2, float* r2, float* m3, float* r3, float* fout, long long ldf,
+                  const float* Wo, const float* bo, const float* gm, const float* bt, const float* W1, const float* b1,
+                  const float* W2, const float* b2, int B, int N, float scale, float p, const unsigned long long* seed_ptr,
+                  unsigned long long seed, unsigned ida, unsigned idb, unsigned idc, unsigned idd, unsigned ide, void* stream);
 size_t hdf_dct_a_bwd_workspace(int R, int Cl);
 int hdf_dct_a_bwd(const float* dqkv, const float* dh1, const float* h0, const float* n1, const float* m1, const float* r1,
                   const float* F, long long ldf, int Cl, const float* Wqkv, const float* gm, const float* Wl, float* dF,

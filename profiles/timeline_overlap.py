@@ -65,9 +65,11 @@ def last(name):
     c = [k for k in ks if name in k[2]]
     return ((c[-1][0] - t0) / 1e3, (c[-1][1] - t0) / 1e3) if c else None
 print("patch-embed gemm (PatchA) first/last:", first("PatchA"), last("PatchA,"))
-af = [k for k in ks if "attn_fwd" in k[2]]
-print("attn_fwd count", len(af), "first start", (af[0][0] - t0) / 1e3, "last end", (af[-1][1] - t0) / 1e3)
-print("dct_c_fwd last end", last("dct_c_fwd"))
+af = [k for k in ks if "attn_fwd" in k[2] or "tok_c_fwd" in k[2]]
+if af:
+    print("attn_fwd / tok_c_fwd count", len(af), "first start", (af[0][0] - t0) / 1e3, "last end", (af[-1][1] - t0) / 1e3)
+print("dct_c_fwd last end", last("dct_c_fwd"), "tok_a_fwd first/last", first("tok_a_fwd"), last("tok_a_fwd"))
+print("tc_conv_ws (start,end)", [(round((k[0] - t0) / 1e3, 3), round((k[1] - t0) / 1e3, 3)) for k in ks if "tc_conv_ws" in k[2]])
 print("upsample2_fwd ends", [round((k[1] - t0) / 1e3, 3) for k in ks if "upsample2_fwd" in k[2]])
 print("maxpool_fwd starts", [round((k[0] - t0) / 1e3, 3) for k in ks if "maxpool_fwd" in k[2]])
 print("first 3 tc_conv_fwd (start,end)", [(round((k[0] - t0) / 1e3, 3), round((k[1] - t0) / 1e3, 3)) for k in ks if "tc_conv_fwd" in k[2]][:8])
@@ -76,11 +78,16 @@ print("attn_bwd first/last", first("attn_bwd"), last("attn_bwd"))
 print("last tc_conv_wgrad end", last("tc_conv_wgrad"))
 print("adam start", first("FusedOptimizer"))
 # per-kernel average in-step duration for the token kernels
+import re as _re
+def _short(n):
+    n = n.replace("(anonymous namespace)::", "").replace("void ", "")
+    m = _re.match(r"([\w:]+)", n)
+    return (m.group(1) if m else n)[:48]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for s, e, n, _ in ks:
-    key = n.split("(")[0][-60:]
+    key = _short(n)
     agg[key][0] += 1; agg[key][1] += (e - s) / 1e3
-for k, (n, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+for k, (n, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{tt:8.2f} ms {n:5d} {1e3*tt/n:8.1f} us  {k}")
 
 # ---- the token-kernel chain of the forward pass: (start ms, duration us, gap to the previous kernel of the same stream us, name)
@@ -94,11 +101,11 @@ for s, e, n, st in sorted(evs):
     streams[st].append((s, e, n))
 print("streams:", {k: len(v) for k, v in streams.items()})
 for st, lst in streams.items():
-    toks = [x for x in lst if any(t in x[2] for t in ("attn", "dct_", "gemm_tile", "layernorm", "reduce_partials", "patch"))]
+    toks = [x for x in lst if any(t in x[2] for t in ("attn", "dct_", "tok_", "gemm_tile", "layernorm", "reduce_partials", "patch"))]
     if len(toks) < 50: continue
     print(f"--- stream {st}: first 40 kernels of the token chain")
     prev = None
-    for s, e, n in lst[:40]:
+    for s, e, n in lst[:int(os.environ.get("HDF_TL_FIRST", "40"))]:
         print(f"  {(s - t0) / 1e3:8.3f} ms  {(e - s):7.1f} us  gap {(s - prev) if prev else 0:7.1f} us  {n}")
         prev = e
     break

@@ -175,7 +175,8 @@ def test_bf16_tensor_core_path_other_configs(in_ch, n_cls, size, batch):
     with nf=16 so every conv takes the tcgen05 path.  These miniature volumes have only 18-24 tokens, so the deep
     InstanceNorms normalise over a handful of voxels and bf16 rounding is amplified (SURVEY 8c pitfall 2: the
     reference's own bf16 autocast is at 1.4e-2 on such sizes); the 2e-2 north-star gate is asserted at 64^3 in
-    test_fp32_and_bf16_vs_oracle_64cube, here the bound is 3e-2 plus gradient alignment with the exact fp32 path."""
+    test_fp32_and_bf16_vs_oracle_64cube and at 96^3 / 144^3 in test_gpu_bench_config.py; here the bound is 4e-2 (the token
+    Linears also run on bf16 operands since round 2) plus gradient alignment with the exact fp32 path."""
     td, nf = 4, 16
     m, sd = build(in_ch, n_cls, nf, size, td)
     m.eval()
@@ -187,7 +188,7 @@ def test_bf16_tensor_core_path_other_configs(in_ch, n_cls, size, batch):
         outs = m(x.to(DEV))
     assert outs[0].dtype == torch.bfloat16 and tuple(outs[3].shape) == (batch, n_cls, *(s // 8 for s in size))
     for o, r in zip(outs, ref):
-        assert rel(o, r) < 3e-2, rel(o, r)
+        assert rel(o, r) < 4e-2, rel(o, r)
     crit(outs, tgt.to(DEV)).backward()
     g16 = {k: p.grad.clone() for k, p in m.named_parameters()}
     m.zero_grad(set_to_none=True)

@@ -382,3 +382,43 @@ def test_upsample_bwd_odd_sizes_slices_and_accumulate():
         acc = base.clone()
         ops.upsample2_bwd(g, acc, True)
         assert rel(acc.float(), base.float() + ref) < 2 * TOL[torch.bfloat16]
+
+
+@pytest.mark.parametrize("B,N,Cl,pdrop", [(2, 729, 128, 0.0), (1, 216, 224, 0.5), (2, 37, 160, 0.5)])
+def test_token_tensor_core_layer_matches_simt_kernels(B, N, Cl, pdrop):
+    """bf16-path tensor-core forward of one DCT inner layer (csrc/tok_tc.cu: mma.sync bf16 Linears, tf32 Q K^T / P V, online
+    softmax in registers) against the fp32 SIMT kernels on the same operands and the same dropout masks.  Tolerance = bf16
+    operand rounding (2^-9 relative per product, fp32 accumulation)."""
+    torch.manual_seed(B * 1000 + N)
+    R = B * N
+    q = "l."
+    names = {"0.weight": (32, Cl), "0.bias": (32,), "1.norm.weight": (32,), "1.norm.bias": (32,), "1.fn.to_qkv.weight": (96, 32),
+             "1.fn.to_out.0.weight": (32, 32), "1.fn.to_out.0.bias": (32,), "2.norm.weight": (32,), "2.norm.bias": (32,),
+             "2.fn.net.0.weight": (64, 32), "2.fn.net.0.bias": (64,), "2.fn.net.3.weight": (32, 64), "2.fn.net.3.bias": (32,)}
+    P = {q + k: (torch.randn(s, device=DEV) * (1.5 / (s[-1] ** 0.5) if len(s) > 1 else 0.1) + (1.0 if k.endswith("norm.weight") else 0.0))
+         for k, s in names.items()}
+    F1 = torch.randn(R, 256, device=DEV)
+    F2 = F1.clone()
+    ids = (3, 4, 5, 6, 7)
+    seed = torch.tensor([13579], dtype=torch.int64, device=DEV)
+    scale = 4 ** -0.5
+    # reference: fp32 SIMT kernels
+    h0, n1, m1, r1, qkv = ops.dct_a_fwd(F1, Cl, P, q)
+    o, lse = ops.attention_fwd(qkv, B, N, 8, scale)
+    sv = ops.dct_c_fwd(o, h0, P, q, F1[:, Cl:Cl + 32], pdrop, seed, ids)
+    # tensor-core kernels
+    h0t, n1t, m1t, r1t, qkvt = ops.tok_a_fwd(F2, Cl, P, q)
+    for a, b, tol in ((h0t, h0, 1e-2), (n1t, n1, 1.5e-2), (qkvt, qkv, 2e-2), (m1t, m1, 2e-2)):
+        assert rel(a, b) < tol, rel(a, b)
+    # attention + chain fed with the SAME qkv / h0 so that only this kernel's arithmetic differs
+    ot, lset, svt = ops.tok_c_fwd(qkv, h0, P, q, F2[:, Cl:Cl + 32], B, N, scale, pdrop, seed, ids)
+    torch.cuda.synchronize()
+    assert rel(ot, o) < 5e-3, rel(ot, o)                    # tf32 scores / probabilities, fp32 statistics
+    assert (lset - lse).abs().max().item() < 2e-2           # tf32 scores: |s| ~ 10 x 2^-11
+    for k in ("h1", "n2", "z1", "f1", "h2", "n3", "z1b", "g1"):
+        assert rel(svt[k], sv[k]) < 3e-2, (k, rel(svt[k], sv[k]))
+    assert rel(F2[:, Cl:Cl + 32], F1[:, Cl:Cl + 32]) < 3e-2
+    assert torch.equal(F2[:, :Cl], F1[:, :Cl]) and torch.equal(F2[:, Cl + 32:], F1[:, Cl + 32:])
+    if pdrop > 0:     # identical masks: the dropped positions coincide (up to gelu underflow at z < -5.9)
+        assert ((svt["f1"] == 0) != (sv["f1"] == 0)).float().mean().item() < 1e-3
+        assert abs((svt["f1"] == 0).float().mean().item() - pdrop) < 0.03
