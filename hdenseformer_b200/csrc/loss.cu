@@ -243,6 +243,45 @@ __global__ void sw_finalize_kernel(float* __restrict__ agg, long long* __restric
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Metric tail (trainer.py:382-398, 919-945; metrics.py:82-151): per-sample confusion matrices of the arg-max masks, one
+// pass over the logits and the one-hot target, no host synchronisation.  conf[b][t][p] += #{voxels: argmax(target) = t,
+// argmax(logits) = p} (first maximal index on ties, like torch.argmax).  compute_dice and RunningDice are derived from it.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) confusion_kernel(const T* __restrict__ logits, const float* __restrict__ target, int C,
+                                                        long long V, unsigned long long* __restrict__ conf) {
+  __shared__ unsigned int s_cnt[MAXCLS * MAXCLS];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const T* lg = logits + (long long)b * C * V;
+  const float* tg = target + (long long)b * C * V;
+  const int lane = threadIdx.x & 31;
+  for (long long v0 = (long long)blockIdx.x * blockDim.x; v0 < V; v0 += (long long)gridDim.x * blockDim.x) {
+    const long long v = v0 + threadIdx.x;
+    int idx = -1;
+    if (v < V) {
+      float bl = to_f(lg[v]), bt = tg[v];
+      int pl = 0, pt = 0;
+      for (int c = 1; c < C; ++c) {
+        const float l = to_f(lg[c * V + v]), t = tg[c * V + v];
+        if (l > bl) { bl = l; pl = c; }
+        if (t > bt) { bt = t; pt = c; }
+      }
+      idx = pt * C + pl;
+    }
+    // the background pair (0, 0) is by far the most frequent: count it with one ballot per warp instead of 32 atomics
+    const unsigned m0 = __ballot_sync(0xffffffffu, idx == 0);
+    if (lane == 0 && m0) atomicAdd(&s_cnt[0], (unsigned)__popc(m0));
+    if (idx > 0) atomicAdd(&s_cnt[idx], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (s_cnt[i]) atomicAdd(&conf[(long long)b * C * C + i], (unsigned long long)s_cnt[i]);
+}
+}  // namespace
+
 extern "C" {
 
 size_t hdf_loss_sums_bytes(int B, int C) { return (size_t)(B * C * 3 + 2) * sizeof(double); }
@@ -319,6 +358,22 @@ int hdf_sw_finalize(float* agg, long long* mask, int C, int X, int Y, int Z, con
   const long long VV = (long long)X * Y * Z;
   sw_finalize_kernel<<<min(148 * 16, cdiv(VV, 256)), 256, 0, (cudaStream_t)stream>>>(agg, mask, C, X, Y, Z, st, normalise);
   HDF_LAUNCH_CHECK("hdf_sw_finalize");
+  return HDF_OK;
+}
+
+// conf [B][C][C] uint64 (+)= per-sample confusion counts (rows = target class, columns = predicted class); conf is NOT
+// zeroed here.  logits [B, C, *] (fp32 / bf16, NCDHW), target one-hot fp32 of the same shape, V = voxels per sample.
+int hdf_confusion_update(int dtype, const void* logits, const float* target, int B, int C, long long V, unsigned long long* conf,
+                         void* stream) {
+  HDF_REQUIRE(logits && target && conf && B >= 1 && C >= 1 && C <= MAXCLS && V >= 1, "hdf_confusion_update: bad args");
+  int gx = (int)((V + 255) / 256);
+  const int cap = (8 * 148 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  dim3 grid(gx, B);
+  HDF_DISPATCH_DTYPE(dtype, T, {
+    confusion_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)logits, target, C, V, conf);
+  });
+  HDF_LAUNCH_CHECK("hdf_confusion_update");
   return HDF_OK;
 }
 

@@ -497,6 +497,15 @@ def loss_level_fwd(logits, target, cw, level, ignore_index, smooth, level_weight
                                        _p(sums), _p(out_level), _p(total), _s()), "loss_level_fwd")
 
 
+def confusion_update(logits: torch.Tensor, target: torch.Tensor, conf: torch.Tensor):
+    """conf [B, C, C] int64 += counts of (argmax target, argmax logits) per sample; asynchronous, no host sync"""
+    B, Cc = logits.shape[:2]
+    V = logits[0, 0].numel()
+    assert conf.dtype == torch.int64 and tuple(conf.shape) == (B, Cc, Cc) and conf.is_contiguous()
+    _C.check(_lib().hdf_confusion_update(_DT[logits.dtype], _p(logits), _p(target), B, Cc, V, _p(conf), _s()), "confusion_update")
+    return conf
+
+
 def loss_level_bwd(logits, target, cw, level, ignore_index, smooth, level_weight, ce_w, dice_w, sums, grad_out, dlogits):
     B, Cc, Dl, Hl, Wl = logits.shape
     has_ig = ignore_index is not None

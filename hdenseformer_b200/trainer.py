@@ -143,22 +143,10 @@ def inference_slidingwindow(net, image, n_cls: int, patch_size: Sequence[int], s
 
 
 def compute_dice(predict: torch.Tensor, target: torch.Tensor, ignore_index: int = 0, smooth: float = 1e-5) -> float:
-    """Hard-mask Dice over foreground classes (trainer.py:891-945); metric tail, host sync, not on the hot path."""
-    op = torch.argmax(predict.float(), dim=1)
-    ot = torch.argmax(target, dim=1)
-    C = target.shape[1]
-    dl = np.ones((C,), dtype=np.float32)
-    for i in range(C):
-        if i == ignore_index:
-            continue
-        a, b = (op == i), (ot == i)
-        if not a.any() and not b.any():
-            continue
-        a = a.float().reshape(a.shape[0], -1)
-        b = b.float().reshape(b.shape[0], -1)
-        d = ((2 * (a * b).sum(1) + smooth) / ((a + b).sum(1) + smooth)).mean()
-        dl[i] = round(d.item(), 4)
-    return float(np.nanmean(dl[1:]))
+    """Hard-mask Dice over foreground classes (trainer.py:891-945), computed on the device from one confusion-count kernel
+    (hdenseformer_b200.metrics); the only host synchronisation is the final read of the scalar."""
+    from . import metrics
+    return metrics.compute_dice(predict, target, ignore_index, smooth)
 
 
 # ----------------------------------------------------------------------------- training

@@ -219,6 +219,10 @@ int hdf_loss_level_bwd(int dtype, const void* logits, const float* target, const
 
 /* ---- sliding-window inference (trainer.py:560-582; cal_steps :595-618 stays host code).
  *      steps_* are HOST arrays of window starts; the count map is analytic, never stored. ---- */
+/* metric tail (trainer.py:382-398, 919-945; metrics.py:82-151): per-sample confusion counts of argmax(target) x
+ * argmax(logits), accumulated into conf [B][C][C] (uint64, caller zeroes); no host synchronisation */
+int hdf_confusion_update(int dtype, const void* logits, const float* target, int B, int C, long long V,
+                         unsigned long long* conf, void* stream);
 int hdf_sw_accumulate(int dtype, const void* logits, float* agg, int C, int X, int Y, int Z, int x0, int y0, int z0, int px,
                       int py, int pz, void* stream);
 int hdf_sw_finalize(float* agg, long long* mask, int C, int X, int Y, int Z, const int* steps_x, int nx, const int* steps_y,

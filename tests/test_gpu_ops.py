@@ -3,6 +3,8 @@ torch fp32 ops of the same semantics (the reference's building blocks).  fp32 pa
 (north_star), bf16 storage path 2e-2."""
 import math
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -422,3 +424,44 @@ def test_token_tensor_core_layer_matches_simt_kernels(B, N, Cl, pdrop):
     if pdrop > 0:     # identical masks: the dropped positions coincide (up to gelu underflow at z < -5.9)
         assert ((svt["f1"] == 0) != (sv["f1"] == 0)).float().mean().item() < 1e-3
         assert abs((svt["f1"] == 0).float().mean().item() - pdrop) < 0.03
+
+
+@pytest.mark.parametrize("C,B,size,dt", [(2, 2, (16, 12, 20), torch.float32), (4, 3, (8, 9, 10), torch.bfloat16), (3, 1, (5, 7, 11), torch.float32)])
+def test_on_device_metric_tail_matches_reference_semantics(C, B, size, dt):
+    """hdf_confusion_update + metrics.compute_dice / RunningDice (no host sync per step) against the restated reference
+    (oracle.compute_dice = trainer.py:919-945; numpy confusion matrix = metrics.py:82-151), incl. a class absent from both
+    masks and a sample whose ground truth is background only."""
+    from oracle import hdf_oracle as O
+    from hdenseformer_b200 import metrics as M
+    torch.manual_seed(C * 10 + B)
+    logits = torch.randn(B, C, *size, device=DEV)
+    if C > 2:
+        logits[:, C - 1] -= 50.0                      # last class never predicted ...
+    lab = torch.randint(0, C - 1 if C > 2 else C, (B, *size), device=DEV)   # ... and never present
+    lab[0] = 0                                        # first sample: background only
+    target = torch.nn.functional.one_hot(lab, C).movedim(-1, 1).float()
+    lg = logits.to(dt)
+    got = M.compute_dice(lg, target)
+    ref = O.compute_dice(lg.float().cpu(), target.cpu())
+    assert abs(got - ref) < 1e-6, (got, ref)
+    conf = M.batch_confusion(lg, target)
+    pred = lg.float().argmax(1)
+    ref_conf = torch.zeros(B, C, C, dtype=torch.int64)
+    for b in range(B):
+        idx = (lab[b].reshape(-1) * C + pred[b].reshape(-1)).cpu()
+        ref_conf[b] = torch.bincount(idx, minlength=C * C).view(C, C)
+    assert torch.equal(conf.cpu(), ref_conf)
+    rd = M.RunningDice(labels=list(range(C)), ignore_label=0)
+    rd.update(lg, target)
+    rd.update(lg[:1], target[:1])                     # all-background ground truth: skipped like the reference
+    rd2 = M.RunningDice(labels=list(range(C)), ignore_label=0)
+    rd2.update_matrix(lab.cpu().numpy(), pred.cpu().numpy())
+    cm = ref_conf.sum(0).numpy()
+    if not (lab != 0).any().item():
+        cm = np.zeros_like(cm)                        # ground truth entirely the ignore label: the batch is skipped
+    assert np.array_equal(rd.overall_confusion_matrix.cpu().numpy(), cm)
+    assert np.array_equal(rd2.overall_confusion_matrix.cpu().numpy(), cm)
+    mean, dl = rd.compute_dice()
+    inter = np.diag(cm); union = cm.sum(0) + cm.sum(1)
+    iou = (2 * inter + 1e-5) / (union.astype(np.float32) + 1e-5)
+    assert abs(mean - float(np.mean(iou[1:]))) < 1e-6 and dl == [round(float(c), 4) for c in iou]
