@@ -1069,6 +1069,15 @@ int hdf_instnorm_stats(int dtype, const void* y, long long ldy, int N, long long
   return HDF_OK;
 }
 
+// mean / rstd from per-chunk partial sums [N][chunks][2][C] (double) written by another kernel (fused conv epilogue)
+int hdf_instnorm_stats_finalize(const double* partial, int chunks, int N, int C, long long V, float eps, float* mean, float* rstd,
+                                void* stream) {
+  HDF_REQUIRE(partial && mean && rstd && chunks >= 1, "hdf_instnorm_stats_finalize: bad args");
+  stats_finalize_kernel<<<cdiv((long long)N * C * 32, 128), 128, 0, (cudaStream_t)stream>>>(partial, chunks, C, V, eps, mean, rstd, N * C);
+  HDF_LAUNCH_CHECK("hdf_instnorm_stats_finalize");
+  return HDF_OK;
+}
+
 int hdf_instnorm_apply(int dtype, const void* y, long long ldy, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, const void* residual, long long ldr, void* out, long long ldo, int N,
                        long long V, int C, int relu, void* stream) {

@@ -51,6 +51,8 @@ struct WsParams {
   const float* bias;
   bf16* y;
   long long ldy;
+  double* stats;                 // optional InstanceNorm partial sums [N][gridDim.x][2][32] (sum, sum of squares of the
+                                 // bf16-rounded outputs per sample and channel), else null
   unsigned long long* dbg;
 };
 
@@ -103,6 +105,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
     }
     tmem_st_wait();
   }
+  // InstanceNorm statistics of the outputs, fused into the epilogue (p.stats != null): the epilogue threads hold one output
+  // channel each, so sum / sum-of-squares accumulate in two registers per thread and meet in shared memory once per sample
+  __shared__ float st_sh[8][WS_COUT][2];
+  for (int i = threadIdx.x; i < 8 * WS_COUT * 2; i += WS_THREADS) (&st_sh[0][0][0])[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -232,10 +238,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
     const uint32_t stg_thr = (uint32_t)(pcol * 64 + c * 2);
     const int xs = pcol >> 1;
     int acc = 0; uint32_t accph = 0;
+    const bool do_stats = p.stats != nullptr;
+    float st1 = 0.f, st2 = 0.f;
+    int n_cur = -1;
+    // partial sums of this thread's channel over the 4 column phases -> shared memory (two adds per address per sample:
+    // the two warps of the quarter; floating-point addition of two values commutes, so the result is deterministic)
+    auto flush_stats = [&](int n) {
+      if (!do_stats || n < 0) return;
+      float a1 = st1, a2 = st2;
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+      if (pcol == 0) { atomicAdd(&st_sh[n][q * 8 + c][0], a1); atomicAdd(&st_sh[n][q * 8 + c][1], a2); }
+      st1 = 0.f; st2 = 0.f;
+    };
     long long e_wait = 0; const long long et0 = p.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int n, d0, d1, h0, w0;
       decode(item, n, d0, d1, h0, w0);
+      if (n != n_cur) { flush_stats(n_cur); n_cur = n; }
       for (int d = d0; d < d1; ++d) {
         const long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(tfull_bar(acc), accph);
@@ -263,7 +283,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
             const float r1 = __shfl_sync(0xffffffffu, send1, src1);     // D1 at column j + 1
             const float r2 = __shfl_sync(0xffffffffu, send2, src2);     // D2 at column j + 2
             const float yv = __uint_as_float(a[2 * g]) + r1 + r2 + bias;
-            *reinterpret_cast<bf16*>(row + (uint32_t)(g * 256) + (uint32_t)((q ^ ((2 * g + xs) & 3)) * 16)) = __float2bfloat16_rn(yv);
+            const bf16 yb = __float2bfloat16_rn(yv);
+            *reinterpret_cast<bf16*>(row + (uint32_t)(g * 256) + (uint32_t)((q ^ ((2 * g + xs) & 3)) * 16)) = yb;
+            if (do_stats && 4 * g + pcol < TWu && w0 + 4 * g + pcol < p.W && h0 + lh < p.H) {
+              const float yr = __bfloat162float(yb);      // statistics of the values the next kernels will read
+              st1 += yr;
+              st2 = fmaf(yr, yr, st2);
+            }
           }
         };
         {
@@ -299,6 +325,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
         }
         // (the other staging buffer is used next; this one is rewritten two tiles later, after another named barrier)
         if (++acc == 2) { acc = 0; accph ^= 1u; }
+      }
+    }
+    if (do_stats) {
+      flush_stats(n_cur);
+      named_bar_sync(1, 256);
+      // partial[((n * chunks + cta) * 2 + which) * 32 + channel], the layout of the stand-alone statistics pass
+      for (int i = etid; i < p.N * 2 * WS_COUT; i += 256) {
+        const int n = i / (2 * WS_COUT), which = (i / WS_COUT) & 1, ch = i % WS_COUT;
+        p.stats[(((size_t)n * gridDim.x + blockIdx.x) * 2 + which) * WS_COUT + ch] = (double)st_sh[n][ch][which];
       }
     }
     if (p.dbg && warp == 2 && lane == 0) {
@@ -340,8 +375,8 @@ int hdf_tc_ws_supported(int mode, int Cin, int Cout) {
 
 // Plan + launch.  Same contract as hdf_tc_conv3d_fwd(mode 0): x [N,D,H,W,Cin] bf16 (channel stride ldx), packed weights
 // [27][32][Cin] bf16, y [N,D,H,W,32] bf16 (channel stride ldy), optional fp32 bias.
-int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy, int N,
-                         int D, int H, int W, int Cin, void* stream) {
+static int ws_launch(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy, int N,
+                     int D, int H, int W, int Cin, double* stats, int* grid_out, void* stream) {
   HDF_REQUIRE(hdf_tc_ws_supported(0, Cin, WS_COUT), "hdf_tc_ws_conv3d_fwd: unsupported Cin=%d", Cin);
   HDF_REQUIRE(x && w_packed_bf16 && y, "hdf_tc_ws_conv3d_fwd: null pointer");
   HDF_REQUIRE((ldx % 8 == 0) && (ldy % 8 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
@@ -405,6 +440,7 @@ int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16
   }
   p.num_items = (int)(cols * p.nSeg);
   p.wp = (const bf16*)w_packed_bf16; p.bias = bias; p.y = (bf16*)y; p.ldy = ldy;
+  p.stats = stats;
   static const char* dbg_env = getenv("HDF_TC_DEBUG");
   static unsigned long long* dbg_buf = nullptr;
   if (dbg_env) {
@@ -425,8 +461,8 @@ int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16
   const size_t smem = (size_t)p.stages * p.stage_bytes + 2 * (size_t)p.stg_bytes + 1024 + 8 * (2 * p.stages + 6) + 64;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));   // + 2 KB static
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
     if (e == cudaSuccess && getenv("HDF_NO_MAX_CARVEOUT") == nullptr) {
       e = cudaFuncSetAttribute(tc_conv_ws_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
       if (e == cudaSuccess)
@@ -436,6 +472,7 @@ int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16
     configured = true;
   }
   const int grid = p.num_items < sms ? p.num_items : sms;
+  if (grid_out) *grid_out = grid;
   if (p.TW == 32) tc_conv_ws_kernel<8><<<grid, WS_THREADS, smem, (cudaStream_t)stream>>>(tmx, p);
   else tc_conv_ws_kernel<4><<<grid, WS_THREADS, smem, (cudaStream_t)stream>>>(tmx, p);
   HDF_LAUNCH_CHECK("hdf_tc_ws_conv3d_fwd");
@@ -447,6 +484,28 @@ int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16
             "epilogue: wait_tfull=%llu total=%llu\n", Cin, p.TH, p.TW, p.NT, p.stages, p.seg_len, p.num_items, h[0], h[1], h[2], h[3], h[4]);
   }
   return HDF_OK;
+}
+
+int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy, int N,
+                         int D, int H, int W, int Cin, void* stream) {
+  return ws_launch(x, ldx, w_packed_bf16, bias, y, ldy, N, D, H, W, Cin, nullptr, nullptr, stream);
+}
+
+// Same convolution with the InstanceNorm statistics of its output (models/HDenseFormer.py:152,168: per (sample, channel)
+// mean and 1/sqrt(biased var + eps) over D*H*W) produced by the epilogue: no separate pass over the 2 x 191 MB output.
+// workspace: hdf_tc_ws_stats_workspace(N) bytes.
+size_t hdf_tc_ws_stats_workspace(int N) { return (size_t)N * 148 * 2 * WS_COUT * sizeof(double); }
+int hdf_instnorm_stats_finalize(const double* partial, int chunks, int N, int C, long long V, float eps, float* mean, float* rstd,
+                                void* stream);
+int hdf_tc_ws_conv3d_fwd_stats(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
+                               int N, int D, int H, int W, int Cin, float eps, float* mean, float* rstd, void* workspace,
+                               size_t ws_bytes, void* stream) {
+  HDF_REQUIRE(mean && rstd && workspace && N >= 1 && N <= 8, "hdf_tc_ws_conv3d_fwd_stats: bad args (N must be <= 8)");
+  HDF_REQUIRE(ws_bytes >= hdf_tc_ws_stats_workspace(N) && hdf_sm_count_cached() <= 148, "hdf_tc_ws_conv3d_fwd_stats: workspace too small");
+  int grid = 0;
+  const int rc = ws_launch(x, ldx, w_packed_bf16, bias, y, ldy, N, D, H, W, Cin, (double*)workspace, &grid, stream);
+  if (rc) return rc;
+  return hdf_instnorm_stats_finalize((const double*)workspace, grid, N, WS_COUT, (long long)D * H * W, eps, mean, rstd, stream);
 }
 
 }  // extern "C"

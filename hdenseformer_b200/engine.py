@@ -99,6 +99,7 @@ class Engine:
         # (34.2 vs 33.1 ms/step), so they stay opt-in
         self.fused_dct_head = os.environ.get("HDF_DCT_HEAD") == "1"
         # bf16 path: tensor-core token kernels (mma.sync Linears / attention) instead of the fp32 SIMT ones
+        self.fuse_in_stats = os.environ.get("HDF_NO_FUSED_STATS") is None   # IN statistics from the WS conv epilogue
         self.tok_tc = os.environ.get("HDF_NO_TOK_TC") is None
         self._tok_bf16 = False
         self.use_side_stream = os.environ.get("HDF_NO_SIDE_STREAM") is None
@@ -237,8 +238,15 @@ class Engine:
         w = P[wkey]
         Cout = w.shape[0]
         y = torch.empty((*x.shape[:-1], Cout), dtype=x.dtype, device=x.device)
-        self._conv_fwd(x, w, P[f"{name}.double_conv.0.bias"] if bias else None, y)
-        mean, rstd = ops.instnorm_stats(y)
+        cb = P[f"{name}.double_conv.0.bias"] if bias else None
+        Cin = w.shape[1]
+        if (self.fuse_in_stats and self.use_tc and x.dtype == torch.bfloat16 and x.shape[-1] == Cin and x.shape[0] <= 8
+                and ops.tc_ws_supported(0, Cin, Cout)):
+            # weight-stationary conv: the InstanceNorm statistics come out of the epilogue (no pass over y)
+            mean, rstd = ops.tc_ws_conv3d_fwd_stats(x, self._pack(w, Cin, Cout, 27, Cin * 27, False, cin_valid=Cin), cb, y)
+        else:
+            self._conv_fwd(x, w, cb, y)
+            mean, rstd = ops.instnorm_stats(y)
         if out is None:
             out = torch.empty_like(y)
         g = P[f"{name}.norm.weight"] if affine else None

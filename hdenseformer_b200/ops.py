@@ -118,6 +118,19 @@ def tc_ws_conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Ten
     return out
 
 
+def tc_ws_conv3d_fwd_stats(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, eps: float = 1e-5):
+    """weight-stationary conv + InstanceNorm statistics of its output from the epilogue.  Returns (mean, rstd) [N, 32]."""
+    N, D, H, W, Cout = out.shape
+    Cin = x.shape[-1]
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and Cout == 32
+    mean = torch.empty((N, Cout), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    ws = Workspace.get(_lib().hdf_tc_ws_stats_workspace(N))
+    _C.check(_lib().hdf_tc_ws_conv3d_fwd_stats(_p(x), _ld(x), _p(wp), _p(bias), _p(out), _ld(out), N, D, H, W, Cin, eps, _p(mean),
+                                               _p(rstd), _p(ws), ws.numel(), _s()), "tc_ws_conv3d_fwd_stats")
+    return mean, rstd
+
+
 def tc_wgrad_supported(mode: int, Cin: int, Cout: int) -> bool:
     return bool(_lib().hdf_tc_wgrad_supported(mode, Cin, Cout))
 

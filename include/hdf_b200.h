@@ -61,6 +61,14 @@ int hdf_tc_conv3d_fwd(int mode, const void* x, long long ldx, const void* w_pack
 int hdf_tc_ws_supported(int mode, int Cin, int Cout);
 int hdf_tc_ws_conv3d_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
                          int N, int D, int H, int W, int Cin, void* stream);
+/* ... and with the InstanceNorm statistics of the output (mean, 1/sqrt(var + eps) per sample and channel, [N][32] fp32)
+ * accumulated in the epilogue; workspace = hdf_tc_ws_stats_workspace(N) bytes, N <= 8 */
+size_t hdf_tc_ws_stats_workspace(int N);
+int hdf_tc_ws_conv3d_fwd_stats(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy,
+                               int N, int D, int H, int W, int Cin, float eps, float* mean, float* rstd, void* workspace,
+                               size_t ws_bytes, void* stream);
+int hdf_instnorm_stats_finalize(const double* partial, int chunks, int N, int C, long long V, float eps, float* mean,
+                                float* rstd, void* stream);
 int hdf_tc_wgrad_supported(int mode, int Cin, int Cout);   /* mode 0 or 1 */
 /* plane-ring weight gradient for stride-1 convs with a 32-channel operand (csrc/tc_wgrad_ws.cu): three w-shifted boxes of
  * the 32-channel operand stacked along M, three line-shifted sub-tiles of the other operand stacked along N, its planes in a
