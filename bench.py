@@ -172,6 +172,9 @@ def conv_class_roofline(ops, batch, size, modalities, dev, timed, pk, nf=32):
             w = torch.randn(ci, co, 27, device=dev) * 0.05
             wp, wpd = ops.tc_pack(w, ci, co, co * 27, 27, False), ops.tc_pack(w, co, ci, 27, co * 27, False)
             fns = {"fwd": lambda i: ops.tc_conv3d_fwd(x, wp, None, y, 1), "dgrad": lambda i: ops.tc_conv3d_fwd(g, wpd, None, dx, 2)}
+            if ops.tc_convt_supported(ci, co):          # upconv_1: the shift-major kernel the engine uses for it
+                wct = ops.tc_convt_pack(w.view(ci, co, 3, 3, 3))
+                fns["fwd"] = lambda i: ops.tc_convt_fwd(x, wct, None, y)
             dw = torch.empty_like(w)
             fns["wgrad"] = lambda i: ops.tc_conv3d_wgrad(x, g, dw, co * 27, 27, 1)
         for cls, fn in fns.items():

@@ -812,6 +812,113 @@ __global__ void __launch_bounds__(256) upsample2_bwd_line_kernel(const bf16* __r
   }
 }
 
+// bf16 fast form of the transpose, register blocked: a CTA produces a 2 x 2 block of input lines (d, h) and a thread the
+// four results of one column (8 channels each) from the 6 x 6 output lines that reach them -- 36 sixteen-byte loads per
+// result instead of the 64 of the gather above, and the CTA reads 9 output lines per input line instead of 16: the
+// gather is bound by L2 -> SM traffic (1.5 GB for the 2 x 144^3 x 32 level, 0.30 ms), not by HBM (0.43 GB).
+// w[i][a]: weight of output offset a (output index 2 x0 - 1 + a) in input x0 + i.
+__device__ __forceinline__ void up2_blk_weights(int x0, int In, float (*w)[6]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int o[4];
+    float t[4];
+    up2_bwd_taps(x0 + i, In, o, t);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const int tap = a - 2 * i;
+      w[i][a] = (tap >= 0 && tap <= 3 && x0 + i < In) ? t[tap < 0 ? 0 : (tap > 3 ? 3 : tap)] : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) upsample2_bwd_blk_kernel(const bf16* __restrict__ dout, long long ldd, bf16* __restrict__ dx,
+                                                               long long lddx, int Di, int Hi, int Wi, int C, int accumulate) {
+  const int cpv = C / 8;
+  const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
+  const int Hb = (Hi + 1) / 2, Db = (Di + 1) / 2;
+  int blk = blockIdx.x;
+  const int hb = blk % Hb; blk /= Hb;
+  const int db = blk % Db;
+  const long long n = blk / Db;
+  const int d0 = 2 * db, h0 = 2 * hb;
+  float wh[2][6];
+  up2_blk_weights(h0, Hi, wh);
+  // the d weights are looked up per plane (the plane loop is not unrolled: 36 unrolled lines spill)
+  __shared__ float wd_sh[2][6];
+  if (threadIdx.x == 0) {
+    float wd[2][6];
+    up2_blk_weights(d0, Di, wd);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int a = 0; a < 6; ++a) wd_sh[i][a] = wd[i][a];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < Wi * cpv; t += blockDim.x) {
+    const int w = t / cpv, c = (t - w * cpv) * 8;
+    int ow[4];
+    float ww[4];
+    up2_bwd_taps(w, Wi, ow, ww);
+    float acc[2][2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][j][e] = 0.f;
+#pragma unroll 1
+    for (int a = 0; a < 6; ++a) {
+      const int od = 2 * d0 - 1 + a;
+      if (od < 0 || od >= Do) continue;
+      const float wd0 = wd_sh[0][a], wd1 = wd_sh[1][a];
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        const int oh = 2 * h0 - 1 + b;
+        if (oh < 0 || oh >= Ho) continue;
+        const bf16* lrow = dout + (((n * Do + od) * Ho + oh) * (long long)Wo) * ldd + c;
+        float v[4][8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (ww[e] != 0.f) load8<bf16>(lrow + (long long)ow[e] * ldd, v[e]);
+        }
+        float s[8];                    // the w taps folded: this line's contribution before the (d, h) weights
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[q] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (ww[e] == 0.f) continue;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) s[q] = fmaf(ww[e], v[e][q], s[q]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (b - 2 * j < 0 || b - 2 * j > 3) continue;
+          const float w0 = wd0 * wh[j][b], w1 = wd1 * wh[j][b];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            acc[0][j][q] = fmaf(w0, s[q], acc[0][j][q]);
+            acc[1][j][q] = fmaf(w1, s[q], acc[1][j][q]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (d0 + i >= Di || h0 + j >= Hi) continue;
+        bf16* row = dx + ((((n * Di + d0 + i) * Hi + h0 + j) * (long long)Wi) + w) * lddx + c;
+        if (accumulate) {
+          float old[8];
+          load8<bf16>(row, old);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[i][j][q] += old[q];
+        }
+        store8<bf16>(row, acc[i][j]);
+      }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // 1x1x1 heads: out[n, k, v] (NCDHW, T) = sum_c a[n, v, c] * w[k, c] + b[k]
 // ---------------------------------------------------------------------------
@@ -1242,7 +1349,11 @@ int hdf_upsample2_bwd(int dtype, const void* dout, long long ldd, void* dx, long
     const size_t line_smem = (size_t)2 * Wi * C * sizeof(float);
     // measured slower than the gather form (0.49 vs 0.30 ms at 144^3: two phases, 18 KB + 99 registers per CTA) -> opt-in
     static const bool ups_v2 = getenv("HDF_UPS_BWD_V2") != nullptr;
-    if (vec && dtype == HDF_BF16 && line_smem <= 48 * 1024 && ups_v2) {
+    static const bool ups_gather = getenv("HDF_UPS_BWD_GATHER") != nullptr;
+    if (vec && dtype == HDF_BF16 && !ups_gather && !ups_v2) {
+      const int Db = (Di + 1) / 2, Hb = (Hi + 1) / 2;
+      upsample2_bwd_blk_kernel<<<(unsigned)((long long)N * Db * Hb), line_block(Wi * (C / 8)), 0, s>>>((const bf16*)dout, ldd, (bf16*)dx, lddx, Di, Hi, Wi, C, accumulate);
+    } else if (vec && dtype == HDF_BF16 && line_smem <= 48 * 1024 && ups_v2) {
       upsample2_bwd_line_kernel<<<(unsigned)((long long)N * Di * Hi), line_block(2 * Wi * (C / 8)), line_smem, s>>>((const bf16*)dout, ldd, (bf16*)dx, lddx, Di, Hi, Wi, C, accumulate);
     } else {
       HDF_VEC_DISPATCH(vec, { upsample2_bwd_kernel<T, VEC><<<(unsigned)((long long)N * Di * Hi), line_block(Wi * (C / VEC)), 0, s>>>((const T*)dout, ldd, (T*)dx, lddx, Di, Hi, Wi, C, accumulate); });

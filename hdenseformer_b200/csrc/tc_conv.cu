@@ -1005,6 +1005,9 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, bf16* __restrict__ o
   }
 }
 
+// (A tiled variant with coalesced 32-byte runs through shared memory was measured SLOWER, 36 vs 26 us per launch: the
+// weights are L2-resident, so the strided 4-byte reads cost no DRAM traffic and the element-wise form has more loads in
+// flight -- profiles/r2_timeline_v5.txt.)
 // ----------------------------------------------------------------------------- stem (first conv, 1..4 input channels)
 // The first layer has only M = 1..4 input channels (block_1_1_left, SURVEY 8d: AI 51, bandwidth-bound).  Zero-padding it
 // to 16 channels costs 9 MMAs with 32-byte rows per 128 voxels (the slowest UMMA operand shape, profiles/r1_umma_probe.txt)

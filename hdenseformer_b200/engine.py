@@ -122,13 +122,20 @@ class Engine:
         """bf16 [27][Cout][Cin] operand tiles of a conv weight; taken from the per-step cache when `_prepack` filled it
         (the consumer's stream then waits for THAT weight's event, not for the whole pre-pack pass)."""
         key = (w.data_ptr(), Cin, Cout, sci, sco, bool(flip), cin_valid)
+        return self._pack_cached(key, w, lambda: ops.tc_pack(w, Cin, Cout, sci, sco, flip, cin_valid=cin_valid))
+
+    def _pack_convt(self, w):
+        """shared-memory image of a ConvTranspose3d(64 -> 32) weight for the shift-major kernel (csrc/tc_convt.cu)"""
+        return self._pack_cached((w.data_ptr(), "convt"), w, lambda: ops.tc_convt_pack(w))
+
+    def _pack_cached(self, key, w, make):
         hit = self._packed.get(key)
         if hit is not None:
             t, ev = hit
             if ev is not None:
                 torch.cuda.current_stream(w.device).wait_event(ev)
             return t
-        t = ops.tc_pack(w, Cin, Cout, sci, sco, flip, cin_valid=cin_valid)
+        t = make()
         if self._packed_open:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(w.device))
@@ -157,7 +164,9 @@ class Engine:
             for k, w in convs:                        # forward layouts
                 if k.startswith("upconv_"):          # ConvTranspose3d weight [Cin, Cout, 27]
                     Cin, Cout = w.shape[0], w.shape[1]
-                    if ops.tc_supported(1, Cin, Cout):
+                    if ops.tc_convt_supported(Cin, Cout):
+                        self._pack_convt(w)
+                    elif ops.tc_supported(1, Cin, Cout):
                         self._pack(w, Cin, Cout, Cout * 27, 27, False)
                 else:                                 # Conv3d weight [Cout, Cin, 27]
                     Cout, Cin = w.shape[0], w.shape[1]
@@ -189,6 +198,8 @@ class Engine:
             wp = ops.conv_pack(w, Cin, Cout, 27, Cin * 27, False)
         else:            # ConvTranspose3d weight [Cin, Cout, 27]
             Cin, Cout = w.shape[0], w.shape[1]
+            if self.use_tc and x.dtype == torch.bfloat16 and x.shape[-1] == Cin and ops.tc_convt_supported(Cin, Cout):
+                return ops.tc_convt_fwd(x, self._pack_convt(w), bias, out)
             if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(1, Cin, Cout):
                 return ops.tc_conv3d_fwd(x, self._pack(w, Cin, Cout, Cout * 27, 27, False), bias, out, mode=1)
             wp = ops.conv_pack(w, Cin, Cout, Cout * 27, 27, False)

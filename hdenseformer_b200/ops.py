@@ -104,6 +104,27 @@ def tc_conv3d_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
+def tc_convt_supported(Cin: int, Cout: int) -> bool:
+    return bool(_lib().hdf_tc_convt_supported(Cin, Cout))
+
+
+def tc_convt_pack(w: torch.Tensor) -> torch.Tensor:
+    """torch ConvTranspose3d weight [64, 32, 3, 3, 3] fp32 -> shared-memory image of the shift-major kernel (bf16)"""
+    assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[:2]) == (64, 32)
+    out = torch.empty(_lib().hdf_tc_convt_packed_bytes() // 2, dtype=torch.bfloat16, device=w.device)
+    _C.check(_lib().hdf_tc_convt_pack_weights(_p(w), _p(out), _s()), "tc_convt_pack")
+    return out
+
+
+def tc_convt_fwd(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor):
+    """ConvTranspose3d(64 -> 32, k3, s2, p1, op1): x [N,D,H,W,64] bf16 -> out [N,2D,2H,2W,32] bf16 (may be a channel slice)"""
+    N, D, H, W, Cin = x.shape
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and Cin == 64
+    assert tuple(out.shape) == (N, 2 * D, 2 * H, 2 * W, 32)
+    _C.check(_lib().hdf_tc_convt_fwd(_p(x), _ld(x), _p(wp), _p(bias), _p(out), _ld(out), N, D, H, W, _s()), "tc_convt_fwd")
+    return out
+
+
 def tc_ws_supported(mode: int, Cin: int, Cout: int) -> bool:
     return bool(_lib().hdf_tc_ws_supported(mode, Cin, Cout))
 

@@ -69,6 +69,17 @@ int hdf_tc_ws_conv3d_fwd_stats(const void* x, long long ldx, const void* w_packe
                                size_t ws_bytes, void* stream);
 int hdf_instnorm_stats_finalize(const double* partial, int chunks, int N, int C, long long V, float eps, float* mean,
                                 float* rstd, void* stream);
+/* shift-major kernel for the big transposed convolution ConvTranspose3d(64 -> 32, k3, s2, p1, op1) = upconv_1
+ * (reference models/HDenseFormer.py:215,249; csrc/tc_convt.cu): 8 shifted input boxes per tile instead of 27 tap boxes, the 8
+ * output parity classes side by side in TMEM.  w is the torch weight [64][32][3][3][3] fp32; the packed buffer
+ * (hdf_tc_convt_packed_bytes() bytes) is the kernel's swizzled shared-memory image.  x [N,D,H,W,64] bf16 -> y [N,2D,2H,2W,32]
+ * bf16 (+ fp32 bias[32]).  HDF_TC_NO_CONVT=1 makes hdf_tc_convt_supported return 0 (callers fall back to mode 1 of
+ * hdf_tc_conv3d_fwd). */
+int hdf_tc_convt_supported(int Cin, int Cout);
+size_t hdf_tc_convt_packed_bytes(void);
+int hdf_tc_convt_pack_weights(const float* w, void* packed_bf16, void* stream);
+int hdf_tc_convt_fwd(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy, int N,
+                     int D, int H, int W, void* stream);
 int hdf_tc_wgrad_supported(int mode, int Cin, int Cout);   /* mode 0 or 1 */
 /* plane-ring weight gradient for stride-1 convs with a 32-channel operand (csrc/tc_wgrad_ws.cu): three w-shifted boxes of
  * the 32-channel operand stacked along M, three line-shifted sub-tiles of the other operand stacked along N, its planes in a

@@ -50,7 +50,11 @@ for name, ci, co, sp, mode in L:
     else:
         w = torch.randn(ci, co, 27, device=dev) * 0.05
         wp = ops.tc_pack(w, ci, co, co * 27, 27, False); wpd = ops.tc_pack(w, co, ci, 27, co * 27, False)
-        tf = timeit(lambda: ops.tc_conv3d_fwd(x, wp, None, y, 1), a.reps)
+        if ops.tc_convt_supported(ci, co):
+            wct = ops.tc_convt_pack(w.view(ci, co, 3, 3, 3))
+            tf = timeit(lambda: ops.tc_convt_fwd(x, wct, None, y), a.reps)
+        else:
+            tf = timeit(lambda: ops.tc_conv3d_fwd(x, wp, None, y, 1), a.reps)
         td = timeit(lambda: ops.tc_conv3d_fwd(g, wpd, None, dx, 2), a.reps)
         dw = torch.empty_like(w)
         tw = timeit(lambda: ops.tc_conv3d_wgrad(x, g, dw, co * 27, 27, 1), a.reps) if ops.tc_wgrad_supported(1, ci, co) else float("nan")

@@ -284,3 +284,50 @@ def test_stem_im2col_gemm_matches_torch(cin, cout, size, N):
     dw = torch.full((cout, cin, 3, 3, 3), 7.0, device=DEV)
     ops.stem_conv_wgrad(xcol, g, dw)
     assert ((dw - wq.grad).abs().max() / wq.grad.abs().max()).item() < 1e-3
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (64, 32), (40, 24), (256, 512)])
+def test_weight_pack_matches_permute(cin, cout):
+    """hdf_tc_pack_weights for the two torch layouts (conv [Cout][Cin][27], conv-transpose [Cin][Cout][27]), plain and
+    tap-flipped, against a permute."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    w = torch.randn(cout, cin, 27, device="cuda", generator=g)
+    ref = w.permute(2, 0, 1).to(torch.bfloat16)                                  # [tap][co][ci]
+    assert torch.equal(ops.tc_pack(w, cin, cout, 27, cin * 27, False).view(27, cout, cin), ref)
+    assert torch.equal(ops.tc_pack(w, cin, cout, 27, cin * 27, True).view(27, cout, cin), ref.flip(0))
+    wt = torch.randn(cin, cout, 27, device="cuda", generator=g)                  # [ci][co][tap]
+    reft = wt.permute(2, 1, 0).to(torch.bfloat16)
+    assert torch.equal(ops.tc_pack(wt, cin, cout, cout * 27, 27, False).view(27, cout, cin), reft)
+    assert torch.equal(ops.tc_pack(wt, cin, cout, cout * 27, 27, True).view(27, cout, cin), reft.flip(0))
+
+
+@pytest.mark.parametrize("size,N", [((4, 4, 8), 1), ((5, 6, 7), 2), ((9, 9, 9), 1), ((12, 8, 16), 2), ((18, 18, 18), 2)])
+def test_shift_major_transposed_conv_matches_torch_and_tap_major_kernel(size, N):
+    """csrc/tc_convt.cu (8 shifted boxes, 8 parity classes in TMEM) for ConvTranspose3d(64 -> 32, k3, s2, p1, op1) =
+    upconv_1 (reference models/HDenseFormer.py:215) against torch fp32 on bf16-rounded operands and against the tap-major
+    kernel (mode 1 of tc_conv3d_fwd); partial tiles in every dim, channel-sliced output like the decoder's cat buffer."""
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    torch.manual_seed(11)
+    cin, cout = 64, 32
+    assert ops.tc_convt_supported(cin, cout)
+    x = torch.randn(N, *size, cin, device=DEV).to(torch.bfloat16)
+    w = torch.randn(cin, cout, 3, 3, 3, device=DEV) / math.sqrt(8 * cin)
+    b = torch.randn(cout, device=DEV)
+    ref = F.conv_transpose3d(x.float().permute(0, 4, 1, 2, 3), w.to(torch.bfloat16).float(), b, stride=2, padding=1,
+                             output_padding=1).permute(0, 2, 3, 4, 1)
+    osz = tuple(2 * s for s in size)
+    buf = torch.zeros(N, *osz, 2 * cout, dtype=torch.bfloat16, device=DEV)
+    y = buf[..., :cout]
+    ops.tc_convt_fwd(x, ops.tc_convt_pack(w), b, y)
+    y_old = torch.empty(N, *osz, cout, dtype=torch.bfloat16, device=DEV)
+    ops.tc_conv3d_fwd(x, ops.tc_pack(w, cin, cout, cout * 27, 27, False), b, y_old, mode=1)
+    torch.cuda.synchronize()
+    err = ((y.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-2, err
+    assert buf[..., cout:].abs().max().item() == 0                  # the other half of the cat buffer is untouched
+    # same products, fp32 accumulation in a different order -> the two kernels agree to bf16 rounding of the output
+    assert ((y.float() - y_old.float()).abs().max() / ref.abs().max()).item() < 1e-2
+    # the second launch re-uses the TMEM / mbarrier protocol state from scratch: identical bits
+    y2 = torch.empty(N, *osz, cout, dtype=torch.bfloat16, device=DEV)
+    ops.tc_convt_fwd(x, ops.tc_convt_pack(w), b, y2)
+    assert torch.equal(y2, y.contiguous())
