@@ -17,7 +17,13 @@ def _lib():
 
 
 def _p(t: Optional[torch.Tensor]):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    # kernels launch on the CURRENT device's current stream (_s, Workspace): an operand on another GPU must fail loudly,
+    # not run on the wrong device (one process per GPU is the supported layout; use torch.cuda.device(...) otherwise)
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise _C.HDFError(f"operand on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}")
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _s():
@@ -562,3 +568,30 @@ def sw_finalize(agg, steps, patch, normalise=True):
     _C.check(_lib().hdf_sw_finalize(_p(agg), _p(mask), Cc, X, Y, Z, arr[0], len(steps[0]), arr[1], len(steps[1]), arr[2],
                                     len(steps[2]), patch[0], patch[1], patch[2], int(normalise), _s()), "sw_finalize")
     return mask
+
+
+# ----------------------------------------------------------------------------- input pipeline (csrc/prep.cu)
+NORM_MODES = {None: 0, "none": 0, "petct": 1, "mr": 2, "trunc": 3}
+
+
+def prep_sample(vol: torch.Tensor, lab: Optional[torch.Tensor], origin, size, norm: Optional[str], p0: float, p1: float,
+                affine: Optional[torch.Tensor], flip_axis: int, num_class: int, img_out: torch.Tensor,
+                lab_out: Optional[torch.Tensor]):
+    """One sample of the fused crop -> normalise -> warp -> flip -> one-hot chain.  vol [M, Dv, Hv, Wv] fp32, lab
+    [Dv, Hv, Wv] fp32 (device, contiguous); affine: device double [3, 4] or None; outputs [M, D, H, W] / [C, D, H, W] fp32."""
+    ensure_init(vol)
+    M, Dv, Hv, Wv = vol.shape
+    D, H, W = size
+    assert vol.dtype == torch.float32 and vol.is_contiguous() and img_out.dtype == torch.float32 and img_out.is_contiguous()
+    assert tuple(img_out.shape) == (M, D, H, W)
+    if lab is not None:
+        assert lab.dtype == torch.float32 and lab.is_contiguous() and tuple(lab.shape) == (Dv, Hv, Wv)
+    if lab_out is not None:
+        assert lab_out.dtype == torch.float32 and lab_out.is_contiguous() and tuple(lab_out.shape) == (num_class, D, H, W)
+    if affine is not None:
+        assert affine.dtype == torch.float64 and affine.is_cuda and affine.is_contiguous() and affine.numel() == 12
+    ws = Workspace.get(_lib().hdf_prep_workspace(M))
+    _C.check(_lib().hdf_prep_sample(_p(vol), _p(lab), M, Dv, Hv, Wv, int(origin[0]), int(origin[1]), int(origin[2]), D, H, W,
+                                    NORM_MODES[norm], float(p0), float(p1), _p(affine), int(flip_axis), int(num_class),
+                                    _p(img_out), _p(lab_out), _p(ws), ws.numel(), _s()), "prep_sample")
+    return img_out, lab_out

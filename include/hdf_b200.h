@@ -258,6 +258,23 @@ int hdf_adam_table_set(void* host_table, int index, float* param, long long offs
 int hdf_adam_step(const void* table, const void* chunks, int nchunks, const float* grad_flat, float* m_flat, float* v_flat,
                   float* hyper, float beta1, float beta2, float eps, int adamw, float grad_scale, void* stream);
 
+/* ---- GPU input pipeline (csrc/prep.cu): one sample of the reference's 3-D transform chain
+ *   RandomCrop3D -> PETandCTNormalize | MRNormalize | Trunc_and_Normalize -> RandomTranslationRotationZoom3D ->
+ *   RandomFlip3D -> To_Tensor   (reference data_utils/transformer_3d.py:7-169, data_utils/data_loader.py:16-68,126-159,
+ *   composed at trainer.py:128-141), fused into a statistics pass over the crop window and one gather kernel.
+ *   vol [M][Dv][Hv][Wv] fp32, lab [Dv][Hv][Wv] fp32 class ids (device); crop origin (d0,h0,w0) size (D,H,W);
+ *   norm_mode 0 none | 1 PET/CT (p0 = CT window centre, p1 = half width; channel 1 z-scored over the crop) | 2 MR (divide
+ *   by the channel maximum, negatives -> 0) | 3 truncate to [p0, p1] and scale to [0, 1];
+ *   affine: DEVICE pointer to the 3 x 4 row-major double matrix (rows 0-2 of compose(T, R, Z)) or null = no warp; the warp
+ *   is skimage.transform.warp(image, coords) = scipy map_coordinates(order 1, mode 'constant', cval 0), labels warped per
+ *   class and thresholded at 0.5; flip_axis 0 none | 1 H | 2 W (applied after the warp);
+ *   img_out [M][D][H][W] fp32; lab_out [num_class][D][H][W] fp32 one-hot, channel 0 = background, or null.
+ *   M, num_class <= 8.  workspace: hdf_prep_workspace(M) bytes. */
+size_t hdf_prep_workspace(int M);
+int hdf_prep_sample(const float* vol, const float* lab, int M, int Dv, int Hv, int Wv, int d0, int h0, int w0, int D, int H, int W,
+                    int norm_mode, float p0, float p1, const double* affine, int flip_axis, int num_class, float* img_out,
+                    float* lab_out, void* workspace, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
