@@ -696,3 +696,13 @@ int hdf_gemm_at_b(const float* A, long long lda, const float* Bm, long long ldb,
 }
 
 }  // extern "C"
+
+// C++-linkage helper for patch_tc.cu: the split-K finishing pass of the patch embedding
+int hdf_patch_finish(const float* part, int S, float* out, long long ldo, const float* bias, const float* pos, int ntok, int E,
+                     long long total, float p, const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id,
+                     void* stream) {
+  patch_finish_kernel<<<min(1024, cdiv(total, 256)), 256, 0, (cudaStream_t)stream>>>(part, S, out, ldo, bias, pos, ntok, E, total, p,
+                                                                                    seed_ptr, seed, call_id);
+  HDF_LAUNCH_CHECK("hdf_patch_embed_tc_fwd/finish");
+  return HDF_OK;
+}

@@ -487,7 +487,8 @@ class Engine:
             F = empty((R, FW), torch.float32)
             tr["pe_id"] = ids()
             ops.patch_embed_fwd(x, i, P[pre + "patch_embeddings.weight"], P[pre + "patch_embeddings.bias"],
-                                P[pre + "position_embeddings"], F[:, :E], p, seed, tr["pe_id"])
+                                P[pre + "position_embeddings"], F[:, :E], p, seed, tr["pe_id"],
+                                tensor_cores=self.tok_tc and self._tok_bf16)
             if side is not None and self.patch_first:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))

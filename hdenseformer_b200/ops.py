@@ -507,9 +507,17 @@ def attention_bwd(qkv, o, dout, lse, B, N, H, scale):
     return dqkv
 
 
-def patch_embed_fwd(img, modality, weight, bias, pos, out, p, seed, call_id):
+def patch_embed_fwd(img, modality, weight, bias, pos, out, p, seed, call_id, tensor_cores=False):
+    """tokens of one modality: Conv3d(1 -> E, k16, s16) + bias + position embedding, dropout.  tensor_cores=True (bf16
+    path): tcgen05 implicit GEMM with bf16 operands (csrc/patch_tc.cu), else the fp32 SIMT GEMM."""
     B, Mch, D, H, W = img.shape
     E = weight.shape[0]
+    if tensor_cores and _lib().hdf_patch_embed_tc_supported(E):
+        ws = Workspace.get(_lib().hdf_patch_embed_tc_workspace(B, D, H, W, E))
+        _C.check(_lib().hdf_patch_embed_tc_fwd(_p(img), B, Mch, modality, D, H, W, _p(weight), _p(bias), _p(pos), _p(out),
+                                               out.stride(0), E, float(p), *_seed_args(seed), call_id, _p(ws), ws.numel(), _s()),
+                 "patch_embed_tc_fwd")
+        return
     ws = Workspace.get(_lib().hdf_patch_embed_fwd_workspace(B, D, H, W, E))
     _C.check(_lib().hdf_patch_embed_fwd(_p(img), B, Mch, modality, D, H, W, _p(weight), _p(bias), _p(pos), _p(out),
                                         out.stride(0), E, float(p), *_seed_args(seed), call_id, _p(ws), ws.numel(), _s()),

@@ -115,6 +115,15 @@ int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, i
                         const float* bias, const float* pos, float* out, long long ldo, int E, float p,
                         const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* workspace,
                         size_t ws_bytes, void* stream);
+/* the same patch embedding as a tcgen05 implicit GEMM (csrc/patch_tc.cu): 128-token A tiles gathered from the fp32 volume into
+ * the swizzled UMMA layout by producer threads, bf16 weights by TMA, fp32 accumulator in TMEM, K split 8 ways; bf16 operand
+ * rounding, same arguments and output as hdf_patch_embed_fwd.  E in {64, 128, 256}. */
+int hdf_patch_embed_tc_supported(int E);
+size_t hdf_patch_embed_tc_workspace(int B, int D, int H, int W, int E);
+int hdf_patch_embed_tc_fwd(const float* img, int B, int Mch, int modality, int D, int H, int W, const float* weight,
+                           const float* bias, const float* pos, float* out, long long ldo, int E, float p,
+                           const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* workspace,
+                           size_t ws_bytes, void* stream);
 /* dropout masks are a pure function of (*seed_ptr + seed, call_id, element index): seed_ptr (nullable) is a device
  * counter the host advances once per forward, so captured CUDA graphs draw fresh masks on every replay */
 size_t hdf_patch_embed_wgrad_workspace(int B, int D, int H, int W, int E);

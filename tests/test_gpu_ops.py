@@ -266,6 +266,31 @@ def test_patch_embed_fwd_wgrad():
     assert rel(dpos, g.view(B, ntok, E).sum(0, keepdim=True)) < 1e-5
 
 
+@pytest.mark.parametrize("B,size,E", [(2, (144, 144, 144), 128), (1, (32, 16, 48), 64), (3, (16, 48, 32), 128), (1, (96, 96, 96), 256)])
+def test_patch_embed_tcgen05_matches_torch_and_simt(B, size, E):
+    """csrc/patch_tc.cu (tcgen05 implicit GEMM: producer-gathered A tiles, TMA weights, split-K 8) against F.conv3d in fp32 on
+    bf16-rounded operands (products exact, only the fp32 accumulation order differs: 1e-5) and against the fp32 SIMT kernel
+    with dropout on: the same counter-based mask must be applied (zeros in the same places)."""
+    torch.manual_seed(B * 7 + E)
+    Mch = 2
+    img = torch.randn(B, Mch, *size, device=DEV)
+    w = torch.randn(E, 1, 16, 16, 16, device=DEV) / 64
+    b = torch.randn(E, device=DEV)
+    ntok = (size[0] // 16) * (size[1] // 16) * (size[2] // 16)
+    pos = torch.randn(1, ntok, E, device=DEV)
+    out = torch.zeros(B * ntok, E + 16, device=DEV)
+    ops.patch_embed_fwd(img, 1, w, b, pos, out[:, :E], 0.0, 0, 0, tensor_cores=True)
+    ref = F.conv3d(img[:, 1:2].bfloat16().float(), w.bfloat16().float(), b, stride=16).flatten(2).transpose(1, 2) + pos
+    assert rel(out[:, :E], ref.reshape(B * ntok, E)) < 1e-5
+    assert out[:, E:].abs().max().item() == 0
+    seed = torch.tensor([4242], dtype=torch.int64, device=DEV)
+    o_tc, o_simt = torch.empty(B * ntok, E, device=DEV), torch.empty(B * ntok, E, device=DEV)
+    ops.patch_embed_fwd(img, 0, w, b, pos, o_tc, 0.5, seed, 9, tensor_cores=True)
+    ops.patch_embed_fwd(img, 0, w, b, pos, o_simt, 0.5, seed, 9, tensor_cores=False)
+    assert torch.equal(o_tc == 0, o_simt == 0)
+    assert rel(o_tc, o_simt) < 1e-2                       # bf16 operand rounding
+
+
 def test_fused_dct_chain_matches_unfused_composition():
     """hdf_dct_c_fwd / hdf_dct_c_bwd (one kernel each) against the same chain composed of single-op kernels, with
     dropout ON (same counter-based masks on both sides) and a ragged row count."""
