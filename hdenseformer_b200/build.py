@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhdf_b200.so")
-SOURCES = ["api.cu", "simt_gemm.cu", "glue.cu", "dct.cu", "loss.cu", "tc_conv.cu", "tc_conv_ws.cu", "tc_wgrad_ws.cu", "tc_convt.cu", "tok_tc.cu", "patch_tc.cu", "prep.cu", "optim.cu"]
+SOURCES = ["api.cu", "simt_gemm.cu", "glue.cu", "dct.cu", "loss.cu", "tc_conv.cu", "tc_conv_ws.cu", "tc_wgrad_ws.cu", "tc_convt.cu", "tok_tc.cu", "stem_tc.cu", "patch_tc.cu", "prep.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # --use_fast_math would change erff/expf/division accuracy on the exact path; keep IEEE math instead.

@@ -1706,3 +1706,10 @@ int hdf_stem_conv_wgrad(const void* xcol_bf16, const void* dy, long long ldy, fl
 }
 
 }  // extern "C"
+
+// C++-linkage helper for stem_tc.cu: partial [S][Kp][Cout] -> dw [Cout][Cin][27]
+int hdf_stem_wgrad_reduce(const float* part, float* dw, int S, int Cin, int Cout, int Kp, int accumulate, void* stream) {
+  stem_wgrad_reduce_kernel<<<cdiv(27ll * Cin * Cout, 128), 128, 0, (cudaStream_t)stream>>>(part, dw, S, Cin, Cout, Kp, accumulate);
+  HDF_LAUNCH_CHECK("hdf_stem_fused_wgrad/reduce");
+  return HDF_OK;
+}

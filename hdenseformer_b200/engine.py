@@ -544,7 +544,9 @@ class Engine:
         # GEMMs have the GPU to themselves instead of queueing behind the 41 k blocks of the first encoder kernels.
         for ev in pe_events:
             main_stream.wait_event(ev)
-        if self.use_tc and self.use_stem and dtype == torch.bfloat16 and ops.stem_supported(M, nf):
+        if self.use_tc and self.use_stem and dtype == torch.bfloat16 and ops.stem_fused_supported(M, nf):
+            xcl = ops.StemInput(x)          # first conv gathers its taps from the fp32 volume itself (csrc/stem_tc.cu)
+        elif self.use_tc and self.use_stem and dtype == torch.bfloat16 and ops.stem_supported(M, nf):
             xcl = ops.stem_im2col(x)        # first conv = one GEMM over the gathered taps (csrc/tc_conv.cu, stem path)
         else:
             pad = 16 if (self.use_tc and dtype == torch.bfloat16 and M < 16 and ops.tc_supported(0, 16, nf)) else 0

@@ -189,19 +189,45 @@ def stem_im2col(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def stem_conv_fwd(xcol: torch.Tensor, w: torch.Tensor, out: torch.Tensor):
-    """w: torch Conv3d weight [Cout, Cin, 3, 3, 3]; out: [N, D, H, W, Cout] bf16 view"""
+class StemInput:
+    """The raw NCDHW fp32 volume standing in for the [N, D, H, W, Kp] bf16 im2col operand of the first convolution: the
+    fused kernels (csrc/stem_tc.cu) gather the taps themselves, so no such matrix exists.  Carries the shape / dtype /
+    device the engine's bookkeeping reads."""
+
+    def __init__(self, x: torch.Tensor):
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 5
+        N, Cin, D, H, W = x.shape
+        self.raw = x
+        self.shape = torch.Size((N, D, H, W, stem_kp(Cin)))
+        self.dtype = torch.bfloat16
+        self.device = x.device
+
+
+def stem_fused_supported(Cin: int, Cout: int) -> bool:
+    return bool(_lib().hdf_stem_fused_supported(Cin, Cout))
+
+
+def stem_conv_fwd(xcol, w: torch.Tensor, out: torch.Tensor):
+    """w: torch Conv3d weight [Cout, Cin, 3, 3, 3]; out: [N, D, H, W, Cout] bf16 view; xcol: im2col matrix or StemInput"""
     N, D, H, W, Cout = out.shape
     Cin = w.shape[1]
     wp = torch.empty((Cout, xcol.shape[-1]), dtype=torch.bfloat16, device=w.device)
     _C.check(_lib().hdf_stem_pack_weights(_p(w), _p(wp), Cin, Cout, _s()), "stem_pack_weights")
+    if isinstance(xcol, StemInput):
+        _C.check(_lib().hdf_stem_fused_fwd(_p(xcol.raw), _p(wp), _p(out), _ld(out), N, Cin, D, H, W, Cout, _s()), "stem_fused_fwd")
+        return out
     _C.check(_lib().hdf_stem_conv_fwd(_p(xcol), _p(wp), _p(out), _ld(out), N, D, H, W, Cin, Cout, _s()), "stem_conv_fwd")
     return out
 
 
-def stem_conv_wgrad(xcol: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, accumulate=False):
+def stem_conv_wgrad(xcol, dy: torch.Tensor, dw: torch.Tensor, accumulate=False):
     N, D, H, W, Cout = dy.shape
     Cin = dw.shape[1]
+    if isinstance(xcol, StemInput):
+        ws = Workspace.get(_lib().hdf_stem_fused_wgrad_workspace(Cin, Cout))
+        _C.check(_lib().hdf_stem_fused_wgrad(_p(xcol.raw), _p(dy), _ld(dy), _p(dw), N, Cin, D, H, W, Cout, _p(ws), ws.numel(),
+                                             int(accumulate), _s()), "stem_fused_wgrad")
+        return
     ws = Workspace.get(_lib().hdf_stem_wgrad_workspace(N, D, H, W, Cin, Cout))
     _C.check(_lib().hdf_stem_conv_wgrad(_p(xcol), _p(dy), _ld(dy), _p(dw), N, D, H, W, Cin, Cout, _p(ws), ws.numel(),
                                         int(accumulate), _s()), "stem_conv_wgrad")

@@ -107,6 +107,17 @@ int hdf_stem_conv_fwd(const void* xcol_bf16, const void* w_packed_bf16, void* y,
 size_t hdf_stem_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout);
 int hdf_stem_conv_wgrad(const void* xcol_bf16, const void* dy, long long ldy, float* dw, int N, int D, int H, int W, int Cin,
                         int Cout, void* workspace, size_t ws_bytes, int accumulate, void* stream);
+/* the same first convolution WITHOUT the im2col matrix (csrc/stem_tc.cu): producer threads assemble the 128-voxel x Kp-tap
+ * operand tile in shared memory straight from the fp32 NCDHW volume (gather -> bf16 -> swizzled UMMA layout); forward reads it
+ * K-major against weights resident in shared memory, the weight gradient reads the same image MN-major against TMA-loaded dY
+ * tiles.  x_ncdhw [N][Cin][D][H][W] fp32; y / dy [N*D*H*W, Cout] bf16 with row stride ldy; w_packed from
+ * hdf_stem_pack_weights.  HDF_NO_STEM_FUSED=1 makes hdf_stem_fused_supported return 0. */
+int hdf_stem_fused_supported(int Cin, int Cout);
+int hdf_stem_fused_fwd(const float* x_ncdhw, const void* w_packed_bf16, void* y, long long ldy, int N, int Cin, int D, int H, int W,
+                       int Cout, void* stream);
+size_t hdf_stem_fused_wgrad_workspace(int Cin, int Cout);
+int hdf_stem_fused_wgrad(const float* x_ncdhw, const void* dy, long long ldy, float* dw, int N, int Cin, int D, int H, int W, int Cout,
+                         void* workspace, size_t ws_bytes, int accumulate, void* stream);
 
 /* ---- patch embedding (nn.Conv3d k16 s16 + position_embeddings + Dropout: models/HDenseFormer.py:115-119,
  *      133-138).  img is the caller's NCDHW fp32 batch; tokens are [B*ntok, E] fp32 rows (ld = ldo). ---- */

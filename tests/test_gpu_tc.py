@@ -286,6 +286,50 @@ def test_stem_im2col_gemm_matches_torch(cin, cout, size, N):
     assert ((dw - wq.grad).abs().max() / wq.grad.abs().max()).item() < 1e-3
 
 
+@pytest.mark.parametrize("cin,cout,size,N", [(2, 32, (16, 16, 16), 2), (1, 16, (8, 12, 20), 1), (3, 32, (16, 24, 40), 1),
+                                             (4, 32, (12, 20, 18), 2), (2, 64, (9, 10, 11), 1), (2, 32, (48, 40, 56), 2),
+                                             (4, 64, (5, 7, 9), 3)])
+def test_stem_fused_gather_matches_torch_and_im2col_path(cin, cout, size, N):
+    """First conv without the im2col matrix (csrc/stem_tc.cu: producer-gathered operand tiles, K-major in the forward,
+    MN-major in the weight gradient): against torch's fp32 conv on bf16-rounded operands, and against the im2col + GEMM
+    path, which multiplies exactly the same bf16 values (fp32 accumulation order differs).  Sizes whose voxel count is not
+    a multiple of the 128-voxel tile and every border case of the 27 taps are included."""
+    ops.ensure_init(torch.zeros(1, device=DEV))
+    assert ops.stem_fused_supported(cin, cout)
+    torch.manual_seed(cin * 11 + cout)
+    x = torch.randn(N, cin, *size, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, 3, device=DEV) / math.sqrt(27 * cin)
+    si = ops.StemInput(x)
+    assert tuple(si.shape) == (N, *size, ops.stem_kp(cin)) and si.dtype == torch.bfloat16
+    buf = torch.zeros(N, *size, cout + 8, dtype=torch.bfloat16, device=DEV)
+    y = buf[..., :cout]
+    ops.stem_conv_fwd(si, w, y)
+    xq = x.to(torch.bfloat16).float()
+    wq = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv3d(xq, wq, None, padding=1)
+    refl = ref.detach().permute(0, 2, 3, 4, 1)
+    assert ((y.float() - refl).abs().max() / refl.abs().max()).item() < 1e-2
+    assert buf[..., cout:].abs().max().item() == 0
+    y_old = torch.empty(N, *size, cout, dtype=torch.bfloat16, device=DEV)
+    xcol = ops.stem_im2col(x)
+    ops.stem_conv_fwd(xcol, w, y_old)
+    assert ((y.float() - y_old.float()).abs().max() / refl.abs().max()).item() < 1e-2
+    g = torch.randn(N, *size, cout, device=DEV).to(torch.bfloat16)
+    ref.backward(g.float().permute(0, 4, 1, 2, 3))
+    dw = torch.full((cout, cin, 3, 3, 3), 7.0, device=DEV)
+    ops.stem_conv_wgrad(si, g, dw)
+    assert ((dw - wq.grad).abs().max() / wq.grad.abs().max()).item() < 1e-3
+    dw2 = dw.clone()
+    ops.stem_conv_wgrad(si, g, dw2, accumulate=True)
+    assert torch.allclose(dw2, 2 * dw, rtol=1e-6, atol=0)
+    # channel-slice dY (row stride != Cout), as in the engine
+    gb = torch.zeros(N, *size, cout + 16, dtype=torch.bfloat16, device=DEV)
+    gb[..., :cout] = g
+    dw3 = torch.empty_like(dw)
+    ops.stem_conv_wgrad(si, gb[..., :cout], dw3)
+    assert torch.equal(dw3, dw)
+
+
 @pytest.mark.parametrize("cin,cout", [(32, 32), (64, 32), (40, 24), (256, 512)])
 def test_weight_pack_matches_permute(cin, cout):
     """hdf_tc_pack_weights for the two torch layouts (conv [Cout][Cin][27], conv-transpose [Cin][Cout][27]), plain and
