@@ -5,7 +5,51 @@
 // fp64 cross-thread reduction of statistics.
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
+
+// Ticket counters for "the last CTA finalises" reductions: 64 zero-initialised counters per (device, stream), handed out on
+// first use.  Launches on one stream are ordered, and the kernels leave every counter at zero again, so a slot is never
+// shared by two reductions in flight -- the same contract as the per-stream partial-sum workspace the callers pass in.  The
+// pool itself is allocated on the first call OUTSIDE stream capture (cudaMalloc is not capturable); until then, and when the
+// pool is exhausted, nullptr is returned and the callers launch their separate finalising kernels.
+// MEASURED SLOWER, therefore opt-in (HDF_FUSED_FINALIZE=1): 95 fewer launches per step (769 -> 674) but 21.65 vs 20.17 ms --
+// the last CTA walks chunks x 2C partials with 8 warps and ~10 dependent L2 round trips per channel (~24 us), where the
+// stand-alone finalising kernel spreads the same walk over N*C warps (~5 us).  profiles/r2_fused_finalize_ab.txt.
+unsigned* hdf_ticket_slot(void* stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, void*>, unsigned*> slots;
+  static std::map<int, std::pair<unsigned*, int>> pools;      // device -> (base, used)
+  constexpr int kSlots = 512, kPer = 64;
+  static const bool on = getenv("HDF_FUSED_FINALIZE") != nullptr;
+  if (!on) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = slots.find({dev, stream});
+  if (it != slots.end()) return it->second;
+  auto& pool = pools[dev];
+  if (!pool.first) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    unsigned* base = nullptr;
+    if (cudaMalloc(&base, (size_t)kSlots * kPer * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(base, 0, (size_t)kSlots * kPer * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    pool = {base, 0};
+  }
+  if (pool.second >= kSlots) return nullptr;
+  unsigned* p = pool.first + (size_t)pool.second * kPer;
+  ++pool.second;
+  slots[{dev, stream}] = p;
+  return p;
+}
+constexpr int HDF_TICKETS_PER_SLOT = 64;
 
 namespace {
 
@@ -33,8 +77,40 @@ bool can_vec(const void* p, long long ld, int C) {
 // generic per-(n,c) two-quantity reduction over V rows.
 // grid (chunks, N), block 256.  partial[n][chunk][2][C] (double)
 // ---------------------------------------------------------------------------
-template <typename T, int VEC, class F>
-__global__ void __launch_bounds__(256) rowreduce_kernel(F f, int V, int C, int rows_per_chunk, double* __restrict__ partial) {
+// What the LAST CTA of a sample does with the per-chunk partials (same summation order as the stand-alone finalising
+// kernels below: lanes stride over the chunks, fixed-order shuffle reduction -> bit-identical results).
+struct FinNone {
+  static constexpr int kind = 0;
+  __device__ void apply(int, int, int, double, double) const {}
+};
+struct FinStats {            // mean / rstd of InstanceNorm
+  static constexpr int kind = 1;
+  long long V; float eps; float* mean; float* rstd;
+  __device__ void apply(int n, int c, int C, double s, double q) const {
+    const double m = s / (double)V;
+    double var = q / (double)V - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[n * C + c] = (float)m;
+    rstd[n * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+};
+struct FinSums {             // s1 / s2 of the InstanceNorm backward (+ gamma / beta gradients once every sample is done)
+  static constexpr int kind = 2;
+  float* s1; float* s2; float* dgamma; float* dbeta; int accumulate;
+  __device__ void apply(int n, int c, int C, double s, double q) const {
+    s1[n * C + c] = (float)s;
+    if (s2) s2[n * C + c] = (float)q;
+  }
+};
+struct FinColSum {           // out[c] (+)= column sum (N = 1)
+  static constexpr int kind = 3;
+  float* out; int accumulate;
+  __device__ void apply(int, int c, int, double s, double) const { out[c] = accumulate ? out[c] + (float)s : (float)s; }
+};
+
+template <typename T, int VEC, class F, class FIN>
+__global__ void __launch_bounds__(256) rowreduce_kernel(F f, int V, int C, int rows_per_chunk, double* __restrict__ partial, FIN fin,
+                                                        unsigned* __restrict__ tickets) {
   extern __shared__ double smd[];  // [2][rows_per_iter][C]
   const int cpv = C / VEC;
   const int rpi = 256 / cpv;  // rows per iteration (>=1 guaranteed by host)
@@ -81,6 +157,46 @@ __global__ void __launch_bounds__(256) rowreduce_kernel(F f, int V, int C, int r
     double s = 0.0;
     for (int rr = 0; rr < rpi; ++rr) s += smd[(q * rpi + rr) * C + c];
     partial[(((long long)n * gridDim.x + chunk) * 2 + q) * C + c] = s;
+  }
+  if (FIN::kind == 0) return;
+  // ---- the last CTA of sample n to get here finalises it (threadFenceReduction pattern)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&tickets[n], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int chunks = gridDim.x, warp = tid >> 5, lane = tid & 31;
+  for (int c = warp; c < C; c += 8) {
+    double s = 0.0, q = 0.0;
+    for (int k = lane; k < chunks; k += 32) {
+      s += __ldcg(partial + (((long long)n * chunks + k) * 2 + 0) * C + c);
+      q += __ldcg(partial + (((long long)n * chunks + k) * 2 + 1) * C + c);
+    }
+    s = warp_sum_d(s);
+    q = warp_sum_d(q);
+    if (lane == 0) fin.apply(n, c, C, s, q);
+  }
+  if (tid == 0) tickets[n] = 0;                       // leave the counter ready for the next launch on this stream
+  if (FIN::kind == 2) {
+    const FinSums& fs = reinterpret_cast<const FinSums&>(fin);
+    if (fs.dgamma == nullptr && fs.dbeta == nullptr) return;
+    // gamma / beta gradients sum s2 / s1 over the samples: done by the CTA that finalises the last sample
+    const int N = gridDim.y;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&tickets[HDF_TICKETS_PER_SLOT - 1], 1u) == (unsigned)N - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = tid; c < C; c += 256) {
+      float a = 0.f, b = 0.f;
+      for (int m = 0; m < N; ++m) { a += __ldcg(fs.s2 + m * C + c); b += __ldcg(fs.s1 + m * C + c); }
+      if (fs.dgamma) fs.dgamma[c] = fs.accumulate ? fs.dgamma[c] + a : a;
+      if (fs.dbeta) fs.dbeta[c] = fs.accumulate ? fs.dbeta[c] + b : b;
+    }
+    if (tid == 0) tickets[HDF_TICKETS_PER_SLOT - 1] = 0;
   }
 }
 
@@ -208,9 +324,9 @@ int reduce_chunks(long long V, int N) {
   return (int)(c < 1 ? 1 : c);
 }
 
-template <typename T, class F>
+template <typename T, class F, class FIN>
 int launch_rowreduce(F f, const void* p0, long long ld0, const void* p1, long long ld1, int N, long long V, int C,
-                     double* partial, int& chunks, cudaStream_t s, const char* name) {
+                     double* partial, int& chunks, cudaStream_t s, const char* name, FIN fin, unsigned* tickets) {
   chunks = reduce_chunks(V, N);
   const int rpc = cdiv(V, chunks);
   chunks = cdiv(V, rpc);
@@ -220,16 +336,19 @@ int launch_rowreduce(F f, const void* p0, long long ld0, const void* p1, long lo
     constexpr int VEC = VecOf<T>::value;
     const int rpi = 256 / (C / VEC);
     const size_t smem = (size_t)2 * rpi * C * sizeof(double);
-    rowreduce_kernel<T, VEC, F><<<grid, 256, smem, s>>>(f, (int)V, C, rpc, partial);
+    rowreduce_kernel<T, VEC, F, FIN><<<grid, 256, smem, s>>>(f, (int)V, C, rpc, partial, fin, tickets);
   } else {
     HDF_REQUIRE(C <= 256, "%s: scalar path supports C <= 256 (C=%d)", name, C);
     const int rpi = 256 / C;
     const size_t smem = (size_t)2 * rpi * C * sizeof(double);
-    rowreduce_kernel<T, 1, F><<<grid, 256, smem, s>>>(f, (int)V, C, rpc, partial);
+    rowreduce_kernel<T, 1, F, FIN><<<grid, 256, smem, s>>>(f, (int)V, C, rpc, partial, fin, tickets);
   }
   HDF_LAUNCH_CHECK(name);
   return HDF_OK;
 }
+
+// ticket slot for a fused finalise, or null (N too large for the slot, pool not available yet, HDF_NO_FUSED_FINALIZE)
+unsigned* fin_tickets(int N, cudaStream_t s) { return N < HDF_TICKETS_PER_SLOT ? hdf_ticket_slot((void*)s) : nullptr; }
 
 // ---------------------------------------------------------------------------
 // elementwise kernels over [N, V, C] vectors
@@ -1166,11 +1285,16 @@ int hdf_instnorm_stats(int dtype, const void* y, long long ldy, int N, long long
   HDF_REQUIRE(y && mean && rstd && workspace && ws_bytes >= hdf_reduce_workspace(N, V, C), "hdf_instnorm_stats: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   int chunks = 0;
+  unsigned* tk = fin_tickets(N, s);
   HDF_DISPATCH_DTYPE(dtype, T, {
     StatsF<T> f{(const T*)y, ldy, V};
-    int rc = launch_rowreduce<T>(f, y, ldy, nullptr, 0, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_stats");
+    int rc = tk ? launch_rowreduce<T>(f, y, ldy, nullptr, 0, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_stats",
+                                      FinStats{V, eps, mean, rstd}, tk)
+                : launch_rowreduce<T>(f, y, ldy, nullptr, 0, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_stats", FinNone{},
+                                      nullptr);
     if (rc) return rc;
   });
+  if (tk) return HDF_OK;
   stats_finalize_kernel<<<cdiv((long long)N * C * 32, 128), 128, 0, s>>>((const double*)workspace, chunks, C, V, eps, mean, rstd, N * C);
   HDF_LAUNCH_CHECK("hdf_instnorm_stats/finalize");
   return HDF_OK;
@@ -1214,16 +1338,22 @@ int hdf_instnorm_bwd(int dtype, const void* dout, long long ldd, const void* y, 
               "hdf_instnorm_bwd: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   int chunks = 0;
+  unsigned* tk = fin_tickets(N, s);
   HDF_DISPATCH_DTYPE(dtype, T, {
     InBwdF<T> f{(const T*)dout, ldd, (const T*)y, ldy, V, mean, rstd, gamma, beta, C, relu};
-    int rc = launch_rowreduce<T>(f, dout, ldd, y, ldy, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_bwd/reduce");
+    int rc = tk ? launch_rowreduce<T>(f, dout, ldd, y, ldy, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_bwd/reduce",
+                                      FinSums{s1, s2, dgamma, dbeta, accumulate_params}, tk)
+                : launch_rowreduce<T>(f, dout, ldd, y, ldy, N, V, C, (double*)workspace, chunks, s, "hdf_instnorm_bwd/reduce",
+                                      FinNone{}, nullptr);
     if (rc) return rc;
   });
-  sums_finalize_kernel<<<cdiv((long long)N * C * 32, 128), 128, 0, s>>>((const double*)workspace, chunks, C, s1, s2, N * C);
-  HDF_LAUNCH_CHECK("hdf_instnorm_bwd/finalize");
-  if (dgamma || dbeta) {
-    in_param_grads_kernel<<<cdiv(C, 128), 128, 0, s>>>(s1, s2, N, C, dgamma, dbeta, accumulate_params);
-    HDF_LAUNCH_CHECK("hdf_instnorm_bwd/params");
+  if (!tk) {
+    sums_finalize_kernel<<<cdiv((long long)N * C * 32, 128), 128, 0, s>>>((const double*)workspace, chunks, C, s1, s2, N * C);
+    HDF_LAUNCH_CHECK("hdf_instnorm_bwd/finalize");
+    if (dgamma || dbeta) {
+      in_param_grads_kernel<<<cdiv(C, 128), 128, 0, s>>>(s1, s2, N, C, dgamma, dbeta, accumulate_params);
+      HDF_LAUNCH_CHECK("hdf_instnorm_bwd/params");
+    }
   }
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(dout, ldd, C) && can_vec<T>(y, ldy, C) && can_vec<T>(dy, ldo, C);
@@ -1246,11 +1376,15 @@ int hdf_colsum(int dtype, const void* x, long long ld, long long rows, int C, fl
   HDF_REQUIRE(x && out && workspace && ws_bytes >= hdf_reduce_workspace(1, rows, C), "hdf_colsum: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   int chunks = 0;
+  unsigned* tk = fin_tickets(1, s);
   HDF_DISPATCH_DTYPE(dtype, T, {
     ColSumF<T> f{(const T*)x, ld, rows};
-    int rc = launch_rowreduce<T>(f, x, ld, nullptr, 0, 1, rows, C, (double*)workspace, chunks, s, "hdf_colsum");
+    int rc = tk ? launch_rowreduce<T>(f, x, ld, nullptr, 0, 1, rows, C, (double*)workspace, chunks, s, "hdf_colsum",
+                                      FinColSum{out, accumulate}, tk)
+                : launch_rowreduce<T>(f, x, ld, nullptr, 0, 1, rows, C, (double*)workspace, chunks, s, "hdf_colsum", FinNone{}, nullptr);
     if (rc) return rc;
   });
+  if (tk) return HDF_OK;
   colsum_finalize_kernel<<<cdiv((long long)C * 32, 128), 128, 0, s>>>((const double*)workspace, chunks, C, out, accumulate);
   HDF_LAUNCH_CHECK("hdf_colsum/finalize");
   return HDF_OK;

@@ -29,6 +29,7 @@
 #include "tc_ptx.cuh"
 
 int hdf_sm_count_cached();
+unsigned* hdf_ticket_slot(void* stream);      // glue.cu
 
 namespace {
 using namespace tcptx;
@@ -53,6 +54,9 @@ struct WsParams {
   long long ldy;
   double* stats;                 // optional InstanceNorm partial sums [N][gridDim.x][2][32] (sum, sum of squares of the
                                  // bf16-rounded outputs per sample and channel), else null
+  unsigned* tickets;             // with stats: non-null -> the last CTA turns the partials into mean / rstd itself
+  float* mean; float* rstd;      // [N][32]
+  float eps; long long V;
   unsigned long long* dbg;
 };
 
@@ -335,6 +339,37 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
         const int n = i / (2 * WS_COUT), which = (i / WS_COUT) & 1, ch = i % WS_COUT;
         p.stats[(((size_t)n * gridDim.x + blockIdx.x) * 2 + which) * WS_COUT + ch] = (double)st_sh[n][ch][which];
       }
+      if (p.tickets) {
+        // the last CTA to get here finalises (same summation order as stats_finalize_kernel in glue.cu: lanes stride over
+        // the CTAs' partials, fixed-order shuffle reduction)
+        __shared__ int ws_last;
+        __threadfence();
+        named_bar_sync(1, 256);
+        if (etid == 0) ws_last = atomicAdd(p.tickets, 1u) == gridDim.x - 1;
+        named_bar_sync(1, 256);
+        if (ws_last) {
+          __threadfence();
+          const int ew = etid >> 5, chunks = gridDim.x;
+          for (int i = ew; i < p.N * WS_COUT; i += 8) {
+            const int n = i / WS_COUT, ch = i % WS_COUT;
+            double sm = 0.0, sq = 0.0;
+            for (int k = lane; k < chunks; k += 32) {
+              sm += __ldcg(p.stats + (((size_t)n * chunks + k) * 2 + 0) * WS_COUT + ch);
+              sq += __ldcg(p.stats + (((size_t)n * chunks + k) * 2 + 1) * WS_COUT + ch);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+            if (lane == 0) {
+              const double m = sm / (double)p.V;
+              double var = sq / (double)p.V - m * m;
+              if (var < 0.0) var = 0.0;
+              p.mean[i] = (float)m;
+              p.rstd[i] = (float)(1.0 / sqrt(var + (double)p.eps));
+            }
+          }
+          if (etid == 0) *p.tickets = 0;
+        }
+      }
     }
     if (p.dbg && warp == 2 && lane == 0) {
       p.dbg[blockIdx.x * 8 + 3] = (unsigned long long)e_wait; p.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - et0);
@@ -375,8 +410,10 @@ int hdf_tc_ws_supported(int mode, int Cin, int Cout) {
 
 // Plan + launch.  Same contract as hdf_tc_conv3d_fwd(mode 0): x [N,D,H,W,Cin] bf16 (channel stride ldx), packed weights
 // [27][32][Cin] bf16, y [N,D,H,W,32] bf16 (channel stride ldy), optional fp32 bias.
+struct WsStatsOut { float* mean; float* rstd; float eps; bool fused; };
+
 static int ws_launch(const void* x, long long ldx, const void* w_packed_bf16, const float* bias, void* y, long long ldy, int N,
-                     int D, int H, int W, int Cin, double* stats, int* grid_out, void* stream) {
+                     int D, int H, int W, int Cin, double* stats, int* grid_out, void* stream, WsStatsOut* so = nullptr) {
   HDF_REQUIRE(hdf_tc_ws_supported(0, Cin, WS_COUT), "hdf_tc_ws_conv3d_fwd: unsupported Cin=%d", Cin);
   HDF_REQUIRE(x && w_packed_bf16 && y, "hdf_tc_ws_conv3d_fwd: null pointer");
   HDF_REQUIRE((ldx % 8 == 0) && (ldy % 8 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
@@ -441,6 +478,11 @@ static int ws_launch(const void* x, long long ldx, const void* w_packed_bf16, co
   p.num_items = (int)(cols * p.nSeg);
   p.wp = (const bf16*)w_packed_bf16; p.bias = bias; p.y = (bf16*)y; p.ldy = ldy;
   p.stats = stats;
+  if (stats && so) {
+    p.tickets = hdf_ticket_slot(stream);
+    p.mean = so->mean; p.rstd = so->rstd; p.eps = so->eps; p.V = (long long)D * H * W;
+    so->fused = p.tickets != nullptr;
+  }
   static const char* dbg_env = getenv("HDF_TC_DEBUG");
   static unsigned long long* dbg_buf = nullptr;
   if (dbg_env) {
@@ -503,8 +545,10 @@ int hdf_tc_ws_conv3d_fwd_stats(const void* x, long long ldx, const void* w_packe
   HDF_REQUIRE(mean && rstd && workspace && N >= 1 && N <= 8, "hdf_tc_ws_conv3d_fwd_stats: bad args (N must be <= 8)");
   HDF_REQUIRE(ws_bytes >= hdf_tc_ws_stats_workspace(N) && hdf_sm_count_cached() <= 148, "hdf_tc_ws_conv3d_fwd_stats: workspace too small");
   int grid = 0;
-  const int rc = ws_launch(x, ldx, w_packed_bf16, bias, y, ldy, N, D, H, W, Cin, (double*)workspace, &grid, stream);
+  WsStatsOut so{mean, rstd, eps, false};
+  const int rc = ws_launch(x, ldx, w_packed_bf16, bias, y, ldy, N, D, H, W, Cin, (double*)workspace, &grid, stream, &so);
   if (rc) return rc;
+  if (so.fused) return HDF_OK;
   return hdf_instnorm_stats_finalize((const double*)workspace, grid, N, WS_COUT, (long long)D * H * W, eps, mean, rstd, stream);
 }
 
