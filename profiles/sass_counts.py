@@ -4,7 +4,7 @@ UTCATOMSWS = tcgen05.alloc, HMMA = mma.sync (token kernels).  Usage: python prof
 import collections, os, re, subprocess
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hdenseformer_b200", "lib")
 PAT = re.compile(r"\b(UTCHMMA|LDTM|STTM|UTMALDG|UTCBAR|UTCATOMSWS|HMMA\.[0-9A-Z.]+|SYNCS\.[A-Z0-9.]+)")
-for obj in ("tc_conv.o", "tc_conv_ws.o", "tc_wgrad_ws.o", "tok_tc.o"):
+for obj in ("tc_conv.o", "tc_conv_ws.o", "tc_wgrad_ws.o", "tc_convt.o", "stem_tc.o", "patch_tc.o", "tok_tc.o"):
     sass = subprocess.run(["cuobjdump", "-sass", os.path.join(LIB, obj)], capture_output=True, text=True).stdout
     fn, cnt = None, collections.Counter()
     for line in sass.splitlines():
