@@ -15,6 +15,7 @@ all-reduce (N>1) + Adam step on one synthetic batch of `--batch` volumes per GPU
                        each layer timed alone with CUDA events) against the measured bf16 peak, plus the largest layer
   sliding_window     : the metric's second half -- ms per 2 x 224^3 volume (27 patches of 144^3, patches sharded over the
                        N ranks, 2 patches per forward), Dice of the bf16 mask against the reference's fp32 mask
+  input_pipeline     : ms per batch for the GPU input pipeline (crop, normalise, affine warp, flip, one-hot) in front of it
   gpu_eager_baseline : the reference module itself, eager cuDNN/cuBLAS under bf16 autocast, train mode, same GPU
 """
 from __future__ import annotations
@@ -206,6 +207,7 @@ def main():
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused=True) instead of the library's FusedAdam")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-sliding-window", action="store_true", help="skip the 2x224^3 sliding-window measurement")
+    ap.add_argument("--no-input-pipeline", action="store_true", help="skip the GPU input-pipeline measurement")
     ap.add_argument("--no-sw-dice", action="store_true", help="skip the fp32 reference mask (Dice) of the sliding-window volume")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch run of the reference module")
     a = ap.parse_args()
@@ -416,6 +418,36 @@ def main():
             sw["mask_mismatch_fraction"] = float((mask.cpu() != ref_mask).float().mean())
             del sdw
 
+    # ---- the stage in front of the path: batches produced by the GPU input pipeline from raw volumes resident
+    # in HBM (crop 176^3 -> 144^3, PET/CT normalise, 'tr' affine warp, flip, one-hot) -- ms per batch of a.batch samples
+    pipe = None
+    if rank == 0 and world == 1 and not a.fp32 and not a.no_input_pipeline and a.modalities == 2 and size == (144, 144, 144):
+        try:
+            import random as _random
+            import numpy as _np
+            from hdenseformer_b200 import data_utils as DU
+            g = torch.Generator(device=dev).manual_seed(11)
+            rawv = torch.randn(2, 176, 176, 176, device=dev, generator=g) * 500
+            rawv[1] = torch.exp(torch.randn(176, 176, 176, device=dev, generator=g))
+            rawl = (torch.rand(176, 176, 176, device=dev, generator=g) > 0.97).float()
+            ds = DU.DataGenerator(DU.ResidentVolumes([{"image": rawv, "label": rawl}] * a.batch), num_class=a.classes,
+                                  transform=DU.Compose([DU.RandomCrop3D(size), DU.PETandCTNormalize(),
+                                                        DU.RandomTranslationRotationZoom3D("tr", a.classes), DU.RandomFlip3D("hv"),
+                                                        DU.To_Tensor(a.classes, 2)]))
+            bi = torch.empty(a.batch, 2, *size, device=dev); bl = torch.empty(a.batch, a.classes, *size, device=dev)
+            _random.seed(0); _np.random.seed(0)
+            idx = list(range(a.batch))
+            for _ in range(3):
+                DU.collate_batch(ds, idx, bi, bl)
+            pms = timed(lambda i: DU.collate_batch(ds, idx, bi, bl), 10) / 10
+            pipe = {"ms_per_batch": pms, "batch": a.batch, "samples_per_s": a.batch / (pms / 1e3),
+                    "what": "hdenseformer_b200.data_utils chain RandomCrop3D(144^3 of 176^3) -> PETandCTNormalize -> "
+                            "RandomTranslationRotationZoom3D('tr') -> RandomFlip3D('hv') -> To_Tensor on HBM-resident raw volumes",
+                    "fraction_of_step": pms / (ms / a.steps)}
+            del rawv, rawl, ds, bi, bl
+        except Exception as e:      # an auxiliary line must never take the benchmark down
+            pipe = {"unavailable": repr(e)[:200]}
+
     # ---- like-for-like GPU comparator: the reference module itself (oracle/_ref), eager cuDNN/cuBLAS, bf16 autocast, train mode
     eager = None
     if rank == 0 and world == 1 and not a.fp32 and not a.no_eager_baseline:
@@ -463,6 +495,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roof,
             "sliding_window": sw,
+            "input_pipeline": pipe,
             "gpu_eager_baseline": eager,
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -43,14 +43,18 @@ def _ld(t: torch.Tensor) -> int:
 
 
 class Workspace:
-    """One growable scratch buffer per (device, stream)."""
+    """One growable scratch buffer per (device, stream).  A buffer that is outgrown is retired, never freed: a captured
+    CUDA graph (GraphedTrainStep, graphed sliding window) may have its address baked into kernel arguments and tensor maps."""
     _bufs = {}
+    _retired = []
 
     @classmethod
     def get(cls, nbytes: int) -> torch.Tensor:
         key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                cls._retired.append(buf)
             buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device="cuda")
             cls._bufs[key] = buf
         return buf
