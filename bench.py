@@ -178,7 +178,13 @@ def conv_class_roofline(ops, batch, size, modalities, dev, timed, pk, nf=32):
                 fns["fwd"] = lambda i: ops.tc_convt_fwd(x, wct, None, y)
             dw = torch.empty_like(w)
             fns["wgrad"] = lambda i: ops.tc_conv3d_wgrad(x, g, dw, co * 27, 27, 1)
+        # passes the tensor-core kernels do not take (e.g. the 256 -> 512 input gradient of up1 with 4 modalities, which the
+        # engine runs on the fp32 SIMT kernel) are left out of the class totals
+        sup = {"fwd": ops.tc_supported(0 if mode == 0 else 1, ci, co), "dgrad": ops.tc_supported(0 if mode == 0 else 2, co, ci),
+               "wgrad": ops.tc_wgrad_supported(mode, ci, co)}
         for cls, fn in fns.items():
+            if not sup[cls]:
+                continue
             fn(0); fn(0)
             ms = timed(fn, 3) / 3
             tot[cls][0] += flop; tot[cls][1] += ms
