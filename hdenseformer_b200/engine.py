@@ -89,7 +89,8 @@ class Engine:
         self._deferred = []
         # stream priorities (lower = more urgent; the graphed trainer captures the main path at -1)
         self.fwd_side_priority = int(os.environ.get("HDF_FWD_SIDE_PRIO", "-2"))
-        self.bwd_side_priority = int(os.environ.get("HDF_BWD_SIDE_PRIO", "0"))
+        self.bwd_side_priority = int(os.environ.get("HDF_BWD_SIDE_PRIO", "-3"))
+        self.wgrad_early = int(os.environ.get("HDF_WGRAD_EARLY", "8"))
         self.prepack = os.environ.get("HDF_NO_PREPACK") is None       # conv weights packed up front on a side stream
         self._packed, self._packed_open = {}, False
         self.patch_first = os.environ.get("HDF_NO_PATCH_FIRST") is None   # encoder starts after the patch-embedding GEMMs
@@ -113,7 +114,7 @@ class Engine:
         at3 join), in the backward pass it has slack and must not steal SM time from the convolution kernels."""
         key = (dev.index if dev.index is not None else torch.cuda.current_device(), idx, phase)
         if key not in self._side:
-            prio = self.fwd_side_priority if phase == "f" else self.bwd_side_priority
+            prio = {"f": self.fwd_side_priority, "w": 0}.get(phase, self.bwd_side_priority)
             self._side[key] = torch.cuda.Stream(device=dev, priority=prio)
         return self._side[key]
 
@@ -276,7 +277,20 @@ class Engine:
         b = P[f"{name}.norm.bias"] if affine else None
         dy = ops.instnorm_bwd(dout, y, mean, rstd, g, b, G[f"{name}.norm.weight"] if affine else None,
                               G[f"{name}.norm.bias"] if affine else None, relu=True)
-        if self.defer_wgrad and self._defer_open:
+        if self.defer_wgrad and self._defer_open and self._early_left > 0:
+            # the first k (HDF_WGRAD_EARLY, default 8) weight gradients of the backward pass start right away on a
+            # low-priority stream, next to the bandwidth-bound InstanceNorm passes of the main stream; the rest stay
+            # deferred as cover for the transformer backward (k = 0 / 8 / 16: 20.24 / 20.10 / 20.27 ms)
+            self._early_left -= 1
+            dev = dy.device
+            ws = self._side_stream(dev, 9, "w")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            ws.wait_event(ev)
+            with torch.cuda.stream(ws):
+                self._conv_wgrad(x, dy, G[wkey])
+            self._early_keep.append((x, dy))
+        elif self.defer_wgrad and self._defer_open:
             self._deferred.append((x, dy, G[wkey], 0, wkey))
         else:
             self._conv_wgrad(x, dy, G[wkey])
@@ -623,6 +637,8 @@ class Engine:
         D, H, W = cfg.image_size
         self._deferred = []
         self._defer_open = self.use_side_stream and self.defer_wgrad   # only useful with a side branch to overlap
+        self._early_left = self.wgrad_early if self._defer_open else 0
+        self._early_keep = []
         # ---- level 0 (full resolution)
         dA = empty(c.a12.shape)
         head_bwd("conv1x1", gout(0, (B, cfg.n_cls, D, H, W)), c.a12, dA, False)
@@ -697,6 +713,9 @@ class Engine:
         # ordered behind the main stream) overlap the remaining weight gradients and the transformer backward.
         order = list(G.keys())
         pos = {k: i for i, k in enumerate(order)}
+        if self._early_keep:
+            main_stream.wait_stream(self._side_stream(dev, 9, "w"))     # early weight gradients are final before any bucket leaves
+            self._early_keep = []
         for j, (wx, wdy, wg, wmode, wkey) in enumerate(self._deferred):
             self._conv_wgrad(wx, wdy, wg, mode=wmode)
             if side is not None:
