@@ -91,6 +91,8 @@ class Engine:
         self.fwd_side_priority = int(os.environ.get("HDF_FWD_SIDE_PRIO", "-2"))
         self.bwd_side_priority = int(os.environ.get("HDF_BWD_SIDE_PRIO", "-3"))
         self.wgrad_early = int(os.environ.get("HDF_WGRAD_EARLY", "8"))
+        self.tok_wgrad_stream = os.environ.get("HDF_NO_TOK_WGRAD_STREAM") is None
+        self._tok_wgrad_stream, self._tok_wgrad_keep = None, []
         self.prepack = os.environ.get("HDF_NO_PREPACK") is None       # conv weights packed up front on a side stream
         self._packed, self._packed_open = {}, False
         self.patch_first = os.environ.get("HDF_NO_PATCH_FIRST") is None   # encoder starts after the patch-embedding GEMMs
@@ -405,6 +407,21 @@ class Engine:
         ops.gemm(dzo_, P[q + "1.fn.to_out.0.weight"], False, do)
         return do, dh
 
+    def _tok_off_chain(self, fn, *keep):
+        """Run a weight-gradient launch of the token branch off its dependency chain: on a second stream that waits for
+        the chain's current position.  The chain is ~100 small dependent kernels per modality and ends the step; the
+        Linear weight / bias gradients hang off it as leaves (HDF_NO_TOK_WGRAD_STREAM=1 keeps them in line)."""
+        ws = self._tok_wgrad_stream
+        if ws is None:
+            return fn()
+        cur = torch.cuda.current_stream(keep[0].device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        ws.wait_event(ev)
+        with torch.cuda.stream(ws):
+            fn()
+        self._tok_wgrad_keep.append(keep)       # operands stay alive until the join at the end of the branch
+
     def _dct_block_bwd(self, P, G, pre, saved, d_o1, R, B, training, seed):
         """d_o1: grad wrt out_layer hidden (after GELU+dropout).  Returns dX = grad wrt block input [R,E] view."""
         E = self.cfg.E
@@ -413,8 +430,8 @@ class Engine:
         dev = F.device
         f32 = torch.float32
         dzo = ops.act_dropout_bwd(d_o1, saved["zo"], 1, p, seed, saved["idf"])
-        ops.gemm_at_b(dzo, F, G[pre + "out_layer.net.0.weight"])
-        ops.colsum(dzo, G[pre + "out_layer.net.0.bias"], accumulate=True)
+        self._tok_off_chain(lambda: (ops.gemm_at_b(dzo, F, G[pre + "out_layer.net.0.weight"]),
+                                     ops.colsum(dzo, G[pre + "out_layer.net.0.bias"], accumulate=True)), dzo, F)
         dF = torch.empty_like(F)
         ops.gemm(dzo, P[pre + "out_layer.net.0.weight"], False, dF)
         scale = (GROWTH // HEADS) ** -0.5
@@ -431,14 +448,14 @@ class Engine:
             if self.fused_dct_head:
                 ops.dct_a_bwd(dqkv, dh, s, F, Cl, dF, P, G, q)
                 continue
-            ops.gemm_at_b(dqkv, s["n1"], G[q + "1.fn.to_qkv.weight"])
+            self._tok_off_chain(lambda dqkv=dqkv, s=s, q=q: ops.gemm_at_b(dqkv, s["n1"], G[q + "1.fn.to_qkv.weight"]), dqkv, s["n1"])
             dn1 = torch.empty((R, GROWTH), dtype=f32, device=dev)
             ops.gemm(dqkv, P[q + "1.fn.to_qkv.weight"], False, dn1)
             ops.layernorm_bwd(dn1, s["h0"], s["m1"], s["r1"], P[q + "1.norm.weight"], dh, True, G[q + "1.norm.weight"],
                               G[q + "1.norm.bias"])
             # h0 = F[:, :Cl] W_l^T + b_l
-            ops.gemm_at_b(dh, F[:, :Cl], G[q + "0.weight"])
-            ops.colsum(dh, G[q + "0.bias"], accumulate=True)
+            self._tok_off_chain(lambda dh=dh, q=q, Cl=Cl: (ops.gemm_at_b(dh, F[:, :Cl], G[q + "0.weight"]),
+                                                          ops.colsum(dh, G[q + "0.bias"], accumulate=True)), dh, F)
             ops.gemm(dh, P[q + "0.weight"], False, dF[:, :Cl], accumulate=True)
         return dF[:, :E]
 
@@ -743,20 +760,27 @@ class Engine:
                 mod_ctx.__enter__()
             dtok = empty((R, E), torch.float32)
             ops.cast_to_f32(dattnall.view(R, E * cfg.M)[:, i * E:(i + 1) * E], dtok)
+            self._tok_wgrad_stream = self._side_stream(dev, 20 + i, "b") if (side is not None and self.tok_wgrad_stream) else None
             for b in reversed(range(cfg.nblocks)):
                 bp = f"{pre}blocks.{b}.0."
                 saved = tr["blocks"][b]
                 dz = ops.act_dropout_bwd(dtok, None, 0, p, c.seed, saved["idg"])
-                ops.gemm_at_b(dz, saved["o1"], G[bp + "out_layer.net.3.weight"])
-                ops.colsum(dz, G[bp + "out_layer.net.3.bias"], accumulate=True)
+                self._tok_off_chain(lambda dz=dz, saved=saved, bp=bp: (ops.gemm_at_b(dz, saved["o1"], G[bp + "out_layer.net.3.weight"]),
+                                                                       ops.colsum(dz, G[bp + "out_layer.net.3.bias"], accumulate=True)),
+                                    dz, saved["o1"])
                 d_o1 = empty((R, 2 * GROWTH), torch.float32)
                 ops.gemm(dz, P[bp + "out_layer.net.3.weight"], False, d_o1)
                 dtok = self._dct_block_bwd(P, G, bp, saved, d_o1, R, B, c.training, c.seed)
             # patch embedding: tok = drop(conv(img) + bias + pos)
             dpe = ops.act_dropout_bwd(dtok, None, 0, p, c.seed, tr["pe_id"])
-            ops.posemb_grad(dpe, G[pre + "position_embeddings"], B, cfg.ntok, E)
-            ops.colsum(dpe, G[pre + "patch_embeddings.bias"])
-            ops.patch_embed_wgrad(c.x, i, dpe, G[pre + "patch_embeddings.weight"])
+            # leaves of the chain: run beside the other modality's chain instead of at the tail of this one
+            self._tok_off_chain(lambda dpe=dpe, pre=pre, i=i: (ops.posemb_grad(dpe, G[pre + "position_embeddings"], B, cfg.ntok, E),
+                                                               ops.colsum(dpe, G[pre + "patch_embeddings.bias"]),
+                                                               ops.patch_embed_wgrad(c.x, i, dpe, G[pre + "patch_embeddings.weight"])),
+                                dpe)
+            if self._tok_wgrad_stream is not None:
+                torch.cuda.current_stream(dev).wait_stream(self._tok_wgrad_stream)
+                self._tok_wgrad_stream, self._tok_wgrad_keep = None, []
             if side is None:
                 notify([k for k in G if k.startswith(pre)][-1])
             if ms is not None:
