@@ -535,6 +535,89 @@ __global__ void __launch_bounds__(256) in_bwd_apply_fast_kernel(const T* __restr
 }
 
 // rows per block for the fast elementwise kernels: ~8 resident-CTA waves over the 148 SMs, >= 4 passes of the block
+// InstanceNorm apply + affine + ReLU fused with the 1x1x1 head that reads its output (models/HDenseFormer.py:253-255: the four
+// deep-supervision heads read the outputs of block_k_2_right / block_4_2_left): the head's dot products are taken from the
+// registers that hold the (bf16-rounded) output row, so the head does not read the 2 x 191 MB activation again.  Thread =
+// (row, 8-channel group) like in_apply_fast_kernel; the C/8 threads of a row combine their partial sums with shuffles.
+__device__ __forceinline__ void unpack8(const uint4& v, float* o) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o[2 * i] = __low2float(h[i]); o[2 * i + 1] = __high2float(h[i]); }
+}
+template <int NC>
+__global__ void __launch_bounds__(256) in_apply_head_kernel(const bf16* __restrict__ y, long long ldy, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, bf16* __restrict__ out, long long ldo,
+                                                           int V, int C, int relu, int rows_per_block,
+                                                           const float* __restrict__ hw, const float* __restrict__ hb,
+                                                           bf16* __restrict__ logits, int ncls) {
+  constexpr int U = 4;
+  const int cpv = C / 8, rpi = 256 / cpv;
+  const int cg = threadIdx.x % cpv, r = threadIdx.x / cpv, n = blockIdx.y, c = cg * 8;
+  float m[8], a[8], gm[8], b[8], wk[NC][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    m[k] = mean[n * C + c + k];
+    a[k] = rstd[n * C + c + k];
+    gm[k] = gamma ? gamma[c + k] : 1.f;
+    b[k] = beta ? beta[c + k] : 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < NC; ++q) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wk[q][k] = q < ncls ? hw[q * C + c + k] : 0.f;
+  }
+  const float bias = (cg < ncls && hb) ? hb[cg] : 0.f;      // thread cg of the row writes class cg
+  const int v0 = blockIdx.x * rows_per_block, v1 = min(V, v0 + rows_per_block);
+  const bf16* yp = y + (long long)n * V * ldy + c;
+  bf16* op = out + (long long)n * V * ldo + c;
+  bf16* lp = logits + (long long)n * ncls * V;
+  auto one = [&](const uint4& ry, int v, bool valid) {
+    float x[8];
+    unpack8(ry, x);
+    uint4 pk;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float z = (x[k] - m[k]) * a[k];           // same operation order as in_apply_fast_kernel
+      z = z * gm[k] + b[k];
+      if (relu) z = fmaxf(z, 0.f);
+      x[k] = z;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    if (valid) *reinterpret_cast<uint4*>(op + (long long)v * ldo) = pk;
+    unpack8(pk, x);                             // the head sees what a separate head kernel would read back: bf16 values
+    float mine = 0.f;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      float sdot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sdot = fmaf(x[k], wk[q][k], sdot);
+      for (int o = cpv >> 1; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+      if (q == cg) mine = sdot;
+    }
+    if (valid && cg < ncls) lp[(long long)cg * V + v] = __float2bfloat16_rn(mine + bias);
+  };
+  // every lane of a warp takes part in the shuffles: rows past the end of the block's range recompute a clamped row and
+  // only their stores are masked (the trip count is uniform over the block)
+  const int v = v0 + r;
+  const int iters = (v1 - v0 + rpi - 1) / rpi;
+  for (int it = 0; it < iters; it += U) {
+    uint4 ry[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int vv = min(v + (it + u) * rpi, V - 1);
+      ry[u] = *reinterpret_cast<const uint4*>(yp + (long long)vv * ldy);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int vv = v + (it + u) * rpi;
+      if (it + u < iters) one(ry[u], vv, vv < v1);
+    }
+  }
+}
+
 inline int fast_rows_per_block(long long V, int N, int rpi) {
   long long target = (148ll * 16 + N - 1) / N;
   long long rpb = (V + target - 1) / target;
@@ -1326,6 +1409,36 @@ int hdf_instnorm_apply(int dtype, const void* y, long long ldy, const float* mea
         } });
   });
   HDF_LAUNCH_CHECK("hdf_instnorm_apply");
+  return HDF_OK;
+}
+
+// 1 if hdf_instnorm_apply_head takes this shape (bf16, C in {16..256} multiple of 8 with C/8 a power of two <= 32, ncls <= 4)
+int hdf_instnorm_apply_head_supported(int C, int ncls) {
+  static const bool off = getenv("HDF_NO_APPLY_HEAD") != nullptr;
+  const int cpv = C / 8;
+  return !off && C % 8 == 0 && cpv >= 1 && cpv <= 32 && (cpv & (cpv - 1)) == 0 && ncls >= 1 && ncls <= 4 && ncls <= cpv;
+}
+
+// out = relu(IN(y) * gamma + beta) (bf16, channel stride ldo)  AND  logits[n, k, v] = head_b[k] + sum_c out[n, v, c] head_w[k, c]
+// (bf16, NCDHW) in one pass over y.  No residual.  Same results as hdf_instnorm_apply followed by hdf_head_fwd up to the
+// fp32 summation order of the 1x1x1 head.
+int hdf_instnorm_apply_head(const void* y, long long ldy, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                            void* out, long long ldo, int N, long long V, int C, int relu, const float* head_w, const float* head_b,
+                            void* logits, int ncls, void* stream) {
+  HDF_REQUIRE(y && mean && rstd && out && head_w && logits, "hdf_instnorm_apply_head: null pointer");
+  HDF_REQUIRE(hdf_instnorm_apply_head_supported(C, ncls), "hdf_instnorm_apply_head: unsupported C=%d ncls=%d", C, ncls);
+  HDF_REQUIRE(can_vec<bf16>(y, ldy, C) && can_vec<bf16>(out, ldo, C) && fast_ok(C, 8, V),
+              "hdf_instnorm_apply_head: operands must be 16-byte aligned channel-vector rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rpb = fast_rows_per_block(V, N, 256 / (C / 8));
+  const dim3 grid((unsigned)cdiv(V, rpb), N);
+  if (ncls <= 2)
+    in_apply_head_kernel<2><<<grid, 256, 0, s>>>((const bf16*)y, ldy, mean, rstd, gamma, beta, (bf16*)out, ldo, (int)V, C, relu, rpb, head_w,
+                                                 head_b, (bf16*)logits, ncls);
+  else
+    in_apply_head_kernel<4><<<grid, 256, 0, s>>>((const bf16*)y, ldy, mean, rstd, gamma, beta, (bf16*)out, ldo, (int)V, C, relu, rpb, head_w,
+                                                 head_b, (bf16*)logits, ncls);
+  HDF_LAUNCH_CHECK("hdf_instnorm_apply_head");
   return HDF_OK;
 }
 

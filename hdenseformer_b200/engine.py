@@ -92,6 +92,7 @@ class Engine:
         self.bwd_side_priority = int(os.environ.get("HDF_BWD_SIDE_PRIO", "-3"))
         self.wgrad_early = int(os.environ.get("HDF_WGRAD_EARLY", "8"))
         self.tok_wgrad_stream = os.environ.get("HDF_NO_TOK_WGRAD_STREAM") is None
+        self.fuse_apply_head = os.environ.get("HDF_NO_APPLY_HEAD") is None
         self._tok_wgrad_stream, self._tok_wgrad_keep = None, []
         self.prepack = os.environ.get("HDF_NO_PREPACK") is None       # conv weights packed up front on a side stream
         self._packed, self._packed_open = {}, False
@@ -246,8 +247,9 @@ class Engine:
             ops.conv3d_wgrad(x, dy, dw, Cout * 27, 27, 1)
 
     # ------------------------------------------------------------------ BasicConv3d / UpConv
-    def _cnr_fwd(self, c: Ctx, name, x, P, out=None, residual=None, affine=True, bias=False, before_apply=None):
-        """conv k3 -> InstanceNorm(+affine) -> ReLU (+ residual).  Saves raw conv output + stats."""
+    def _cnr_fwd(self, c: Ctx, name, x, P, out=None, residual=None, affine=True, bias=False, before_apply=None, head=None):
+        """conv k3 -> InstanceNorm(+affine) -> ReLU (+ residual).  Saves raw conv output + stats.  head = (weight, bias) of a
+        1x1x1 head reading the output: returns (out, logits), fused into the apply pass where the kernel takes the shape."""
         wkey = f"{name}.conv.weight" if affine else f"{name}.double_conv.0.weight"
         w = P[wkey]
         Cout = w.shape[0]
@@ -267,8 +269,13 @@ class Engine:
         b = P[f"{name}.norm.bias"] if affine else None
         if before_apply is not None:
             residual = before_apply()
-        ops.instnorm_apply(y, mean, rstd, g, b, out, residual=residual, relu=True)
         setattr(c, name, (x, y, mean, rstd))
+        if head is not None:
+            if residual is None and self.fuse_apply_head and ops.instnorm_apply_head_supported(y, head[0].shape[0]):
+                return out, ops.instnorm_apply_head(y, mean, rstd, g, b, out, head[0], head[1], relu=True)
+            ops.instnorm_apply(y, mean, rstd, g, b, out, residual=residual, relu=True)
+            return out, ops.head_fwd(out, head[0], head[1])
+        ops.instnorm_apply(y, mean, rstd, g, b, out, residual=residual, relu=True)
         return out
 
     def _cnr_bwd(self, c: Ctx, name, dout, P, G, affine=True, bias=False, need_dx=True):
@@ -604,16 +611,13 @@ class Engine:
         out3 = ops.head_fwd(x4, P["conv1x1_d3.weight"], P["conv1x1_d3.bias"])
         self._conv_fwd(x4, P["upconv_3.weight"], P["upconv_3.bias"], cat3[..., :4 * nf], mode=1)
         a = self._cnr_fwd(c, "block_3_1_right", cat3, P)
-        a32 = self._cnr_fwd(c, "block_3_2_right", a, P)
-        out2 = ops.head_fwd(a32, P["conv1x1_d2.weight"], P["conv1x1_d2.bias"])
+        a32, out2 = self._cnr_fwd(c, "block_3_2_right", a, P, head=(P["conv1x1_d2.weight"], P["conv1x1_d2.bias"]))
         self._conv_fwd(a32, P["upconv_2.weight"], P["upconv_2.bias"], cat2[..., :2 * nf], mode=1)
         a = self._cnr_fwd(c, "block_2_1_right", cat2, P)
-        a22 = self._cnr_fwd(c, "block_2_2_right", a, P)
-        out1 = ops.head_fwd(a22, P["conv1x1_d1.weight"], P["conv1x1_d1.bias"])
+        a22, out1 = self._cnr_fwd(c, "block_2_2_right", a, P, head=(P["conv1x1_d1.weight"], P["conv1x1_d1.bias"]))
         self._conv_fwd(a22, P["upconv_1.weight"], P["upconv_1.bias"], cat1[..., :nf], mode=1)
         a = self._cnr_fwd(c, "block_1_1_right", cat1, P)
-        a12 = self._cnr_fwd(c, "block_1_2_right", a, P)
-        out0 = ops.head_fwd(a12, P["conv1x1.weight"], P["conv1x1.bias"])
+        a12, out0 = self._cnr_fwd(c, "block_1_2_right", a, P, head=(P["conv1x1.weight"], P["conv1x1.bias"]))
         c.a32, c.a22, c.a12 = a32, a22, a12
         return [out0, out1, out2, out3], (c if save else None)
 

@@ -258,6 +258,21 @@ def instnorm_apply(y, mean, rstd, gamma, beta, out, residual=None, relu=True):
     return out
 
 
+def instnorm_apply_head_supported(y: torch.Tensor, ncls: int) -> bool:
+    return y.dtype == torch.bfloat16 and bool(_lib().hdf_instnorm_apply_head_supported(y.shape[-1], ncls))
+
+
+def instnorm_apply_head(y, mean, rstd, gamma, beta, out, head_w, head_b, relu=True):
+    """InstanceNorm apply (+affine, ReLU) and the 1x1x1 head on its output in one pass; returns the logits [N, ncls, D, H, W]"""
+    N, C = y.shape[0], y.shape[-1]
+    V = y.numel() // (N * C)
+    ncls = head_w.shape[0]
+    logits = torch.empty((N, ncls, *y.shape[1:4]), dtype=y.dtype, device=y.device)
+    _C.check(_lib().hdf_instnorm_apply_head(_p(y), _ld(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(out), _ld(out), N, V, C,
+                                            int(relu), _p(head_w), _p(head_b), _p(logits), ncls, _s()), "instnorm_apply_head")
+    return logits
+
+
 def instnorm_bwd(dout, y, mean, rstd, gamma, beta, dgamma, dbeta, relu=True, accumulate_params=False):
     N, C = y.shape[0], y.shape[-1]
     V = y.numel() // (N * C)

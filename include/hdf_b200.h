@@ -211,6 +211,12 @@ int hdf_instnorm_stats(int dtype, const void* y, long long ldy, int N, long long
 int hdf_instnorm_apply(int dtype, const void* y, long long ldy, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, const void* residual, long long ldr, void* out, long long ldo, int N,
                        long long V, int C, int relu, void* stream);
+/* ... fused with the 1x1x1 head that consumes its output (reference models/HDenseFormer.py:253-255 after :152-158): out as
+ * above (no residual) AND logits [N, ncls, V] bf16 = head_b + out . head_w^T from the same registers; bf16 only, ncls <= 4 */
+int hdf_instnorm_apply_head_supported(int C, int ncls);
+int hdf_instnorm_apply_head(const void* y, long long ldy, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                            void* out, long long ldo, int N, long long V, int C, int relu, const float* head_w, const float* head_b,
+                            void* logits, int ncls, void* stream);
 int hdf_instnorm_bwd(int dtype, const void* dout, long long ldd, const void* y, long long ldy, const float* mean,
                      const float* rstd, const float* gamma, const float* beta, void* dy, long long ldo, int N, long long V,
                      int C, int relu, float* s1, float* s2, float* dgamma, float* dbeta, int accumulate_params,

@@ -490,3 +490,28 @@ def test_on_device_metric_tail_matches_reference_semantics(C, B, size, dt):
     inter = np.diag(cm); union = cm.sum(0) + cm.sum(1)
     iou = (2 * inter + 1e-5) / (union.astype(np.float32) + 1e-5)
     assert abs(mean - float(np.mean(iou[1:]))) < 1e-6 and dl == [round(float(c), 4) for c in iou]
+
+
+@pytest.mark.parametrize("C,ncls,V", [(32, 2, 4097), (64, 2, 729), (128, 4, 200), (16, 2, 130), (256, 3, 77)])
+def test_instnorm_apply_fused_with_head_matches_separate_kernels(C, ncls, V):
+    """hdf_instnorm_apply_head (one pass) against hdf_instnorm_apply followed by hdf_head_fwd: the activation is bit-identical,
+    the logits differ only by the fp32 summation order of the 1x1x1 head (then bf16 rounding); ragged row counts exercise
+    the masked tail where whole warps still take part in the shuffles."""
+    torch.manual_seed(C + ncls)
+    N = 2
+    y = torch.randn(N, V, 1, 1, C, device=DEV).to(torch.bfloat16)
+    assert ops.instnorm_apply_head_supported(y, ncls)
+    mean, rstd = ops.instnorm_stats(y)
+    gm, bt = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    hw, hb = torch.randn(ncls, C, 1, 1, 1, device=DEV) / C ** 0.5, torch.randn(ncls, device=DEV)
+    buf = torch.zeros(N, V, 1, 1, C + 8, dtype=torch.bfloat16, device=DEV)
+    out = buf[..., :C]
+    logits = ops.instnorm_apply_head(y, mean, rstd, gm, bt, out, hw, hb, relu=True)
+    ref_out = torch.empty_like(y)
+    ops.instnorm_apply(y, mean, rstd, gm, bt, ref_out, relu=True)
+    ref_logits = ops.head_fwd(ref_out, hw, hb)
+    assert torch.equal(out, ref_out) and buf[..., C:].abs().max().item() == 0
+    assert logits.shape == ref_logits.shape
+    assert rel(logits.float(), ref_logits.float()) < 1e-2
+    exact = torch.einsum("nvc,kc->nkv", ref_out.view(N, V, C).float(), hw.view(ncls, C)) + hb.view(1, ncls, 1)
+    assert rel(logits.float().view(N, ncls, V), exact) < 1e-2
