@@ -36,12 +36,14 @@ def param_shapes(in_channels: int, n_cls: int, n_filters: int, image_size: Seque
     nf = n_filters
     E = 4 * nf
     g = 32  # growth_rate default, models/HDenseFormer.py:79
-    N = (image_size[0] // 16) * (image_size[1] // 16) * (image_size[2] // 16)
+    nd = len(image_size)          # 3: models/HDenseFormer.py; 2: models/HDenseFormer_2D.py (same graph, 2-D layers)
+    N = int(np.prod([s // 16 for s in image_size]))
+    k3, k16, k1 = (3,) * nd, (16,) * nd, (1,) * nd
     out: Dict[str, tuple] = {}
     for i in range(in_channels):
         p = f"attns.{i}."
         out[p + "position_embeddings"] = (1, N, E)
-        out[p + "patch_embeddings.weight"] = (E, 1, 16, 16, 16)
+        out[p + "patch_embeddings.weight"] = (E, 1) + k16
         out[p + "patch_embeddings.bias"] = (E,)
         for b in range(transformer_depth // 4):
             q = p + f"blocks.{b}.0."
@@ -66,20 +68,20 @@ def param_shapes(in_channels: int, n_cls: int, n_filters: int, image_size: Seque
             out[q + "out_layer.net.3.bias"] = (E,)
 
     def upconv(name, ci, co):
-        out[f"{name}.double_conv.0.weight"] = (co, ci, 3, 3, 3)
+        out[f"{name}.double_conv.0.weight"] = (co, ci) + k3
         out[f"{name}.double_conv.0.bias"] = (co,)
 
     def basic(name, ci, co):
-        out[f"{name}.conv.weight"] = (co, ci, 3, 3, 3)
+        out[f"{name}.conv.weight"] = (co, ci) + k3
         out[f"{name}.norm.weight"] = (co,)
         out[f"{name}.norm.bias"] = (co,)
 
     def convt(name, ci, co):
-        out[f"{name}.weight"] = (ci, co, 3, 3, 3)
+        out[f"{name}.weight"] = (ci, co) + k3
         out[f"{name}.bias"] = (co,)
 
     def head(name, ci):
-        out[f"{name}.weight"] = (n_cls, ci, 1, 1, 1)
+        out[f"{name}.weight"] = (n_cls, ci) + k1
         out[f"{name}.bias"] = (n_cls,)
 
     upconv("deep_conv", E * in_channels, 8 * nf)
@@ -127,8 +129,8 @@ def synth_state_dict(shapes: Dict[str, tuple], seed: int = 0, dtype=torch.float3
             t = 0.05 * torch.randn(shp, generator=g)
         else:
             fan_in = int(np.prod(shp[1:]))
-            if "upconv_" in k:  # ConvTranspose3d weight is [Cin,Cout,k,k,k]; each output sees <= 8 taps
-                fan_in = shp[0] * 8
+            if "upconv_" in k:  # ConvTranspose weight is [Cin,Cout,k,..]; each output sees <= 2^nd taps
+                fan_in = shp[0] * 2 ** (len(shp) - 2)
             t = torch.randn(shp, generator=g) * (1.0 / math.sqrt(fan_in))
         sd[k] = t.to(dtype)
     return sd
@@ -149,21 +151,20 @@ def synth_mr(batch: int, channels: int, size: Sequence[int], seed: int = 0) -> t
     (data_utils/data_loader.py:39-50)."""
     g = torch.Generator().manual_seed(2000 + seed)
     x = torch.rand((batch, channels, *size), generator=g) ** 2
-    return (x / x.amax(dim=(2, 3, 4), keepdim=True)).float()
+    return (x / x.amax(dim=tuple(range(2, 2 + len(size))), keepdim=True)).float()
 
 
 def synth_label(batch: int, n_cls: int, size: Sequence[int], seed: int = 0) -> torch.Tensor:
     """One-hot f32 label [B,C,D,H,W], channel 0 = background, one seeded ellipsoid per
     foreground class (contract of data_utils/data_loader.py:146-151)."""
     rng = np.random.RandomState(3000 + seed)
-    D, H, W = size
-    zz, yy, xx = np.meshgrid(np.arange(D), np.arange(H), np.arange(W), indexing="ij")
-    lab = np.zeros((batch, D, H, W), dtype=np.int64)
+    grids = np.meshgrid(*[np.arange(s) for s in size], indexing="ij")      # 3-D volumes or 2-D slices
+    lab = np.zeros((batch, *size), dtype=np.int64)
     for b in range(batch):
         for c in range(1, n_cls):
             ctr = [rng.uniform(0.3, 0.7) * s for s in size]
             rad = [rng.uniform(0.12, 0.25) * s for s in size]
-            m = ((zz - ctr[0]) / rad[0]) ** 2 + ((yy - ctr[1]) / rad[1]) ** 2 + ((xx - ctr[2]) / rad[2]) ** 2 <= 1
+            m = sum(((g - ctr[i]) / rad[i]) ** 2 for i, g in enumerate(grids)) <= 1
             lab[b][m] = c
     oh = np.stack([(lab == c) for c in range(n_cls)], 1).astype(np.float32)
     return torch.from_numpy(oh)
@@ -214,19 +215,28 @@ def _dct_block(sd, p, x, drop):
 def _transformer_branch(sd, p, img, n_blocks, drop):
     """Dense_TransformerBlock.forward (models/HDenseFormer.py:132-145).  The trailing
     F.interpolate to the same size is nearest -> identity (SURVEY.md 2.1 K8')."""
-    x = F.conv3d(img, sd[p + "patch_embeddings.weight"], sd[p + "patch_embeddings.bias"], stride=16)
-    B, E, d, h, w = x.shape
+    x = _conv(img, sd[p + "patch_embeddings.weight"], sd[p + "patch_embeddings.bias"], stride=16)
+    shp = x.shape
     x = x.flatten(2).transpose(-1, -2)
     x = drop(x + sd[p + "position_embeddings"])
     for b in range(n_blocks):
         x = _dct_block(sd, p + f"blocks.{b}.0.", x, drop)
-    return x.transpose(1, 2).reshape(B, E, d, h, w)
+    return x.transpose(1, 2).reshape(shp)
+
+
+def _conv(x, w, b=None, **kw):
+    """nn.Conv3d (models/HDenseFormer.py) or nn.Conv2d (models/HDenseFormer_2D.py, the same graph with 2-D layers)"""
+    return (F.conv2d if x.dim() == 4 else F.conv3d)(x, w, b, **kw)
+
+
+def _pool(x):
+    return F.max_pool2d(x, 2, 2) if x.dim() == 4 else F.max_pool3d(x, 2, 2)
 
 
 def _basic(sd, name, x):
     """BasicConv3d: conv k3 p1 no bias -> InstanceNorm3d(affine) -> ReLU
     (models/HDenseFormer.py:148-159)."""
-    x = F.conv3d(x, sd[name + ".conv.weight"], None, padding=1)
+    x = _conv(x, sd[name + ".conv.weight"], None, padding=1)
     x = F.instance_norm(x, weight=sd[name + ".norm.weight"], bias=sd[name + ".norm.bias"], eps=1e-5)
     return F.relu(x)
 
@@ -234,18 +244,19 @@ def _basic(sd, name, x):
 def _upconv(sd, name, x):
     """UpConv: conv k3 p1 bias -> InstanceNorm3d(no affine) -> ReLU -> trilinear x2
     (models/HDenseFormer.py:162-175)."""
-    x = F.conv3d(x, sd[name + ".double_conv.0.weight"], sd[name + ".double_conv.0.bias"], padding=1)
+    x = _conv(x, sd[name + ".double_conv.0.weight"], sd[name + ".double_conv.0.bias"], padding=1)
     x = F.relu(F.instance_norm(x, eps=1e-5))
-    return F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+    return F.interpolate(x, scale_factor=2, mode="bilinear" if x.dim() == 4 else "trilinear", align_corners=False)
 
 
 def _convt(sd, name, x):
     """nn.ConvTranspose3d k3 s2 p1 op1 (models/HDenseFormer.py:211,215,219)."""
-    return F.conv_transpose3d(x, sd[name + ".weight"], sd[name + ".bias"], stride=2, padding=1, output_padding=1)
+    ct = F.conv_transpose2d if x.dim() == 4 else F.conv_transpose3d
+    return ct(x, sd[name + ".weight"], sd[name + ".bias"], stride=2, padding=1, output_padding=1)
 
 
 def _head(sd, name, x):
-    return F.conv3d(x, sd[name + ".weight"], sd[name + ".bias"])
+    return _conv(x, sd[name + ".weight"], sd[name + ".bias"])
 
 
 def forward(sd: StateDict, x: torch.Tensor, transformer_depth: int = 12, dropout_p: float = 0.0,
@@ -266,9 +277,9 @@ def forward(sd: StateDict, x: torch.Tensor, transformer_depth: int = 12, dropout
     at2 = _upconv(sd, "up2", at1)
     at3 = _upconv(sd, "up3", at2)
     ds0 = _basic(sd, "block_1_2_left", _basic(sd, "block_1_1_left", x)) + at3
-    ds1 = _basic(sd, "block_2_2_left", _basic(sd, "block_2_1_left", F.max_pool3d(ds0, 2, 2))) + at2
-    ds2 = _basic(sd, "block_3_2_left", _basic(sd, "block_3_1_left", F.max_pool3d(ds1, 2, 2))) + at1
-    y = _basic(sd, "block_4_2_left", _basic(sd, "block_4_1_left", F.max_pool3d(ds2, 2, 2))) + attnout
+    ds1 = _basic(sd, "block_2_2_left", _basic(sd, "block_2_1_left", _pool(ds0))) + at2
+    ds2 = _basic(sd, "block_3_2_left", _basic(sd, "block_3_1_left", _pool(ds1))) + at1
+    y = _basic(sd, "block_4_2_left", _basic(sd, "block_4_1_left", _pool(ds2))) + attnout
     out3 = _head(sd, "conv1x1_d3", y)
     y = _basic(sd, "block_3_2_right", _basic(sd, "block_3_1_right", torch.cat([_convt(sd, "upconv_3", y), ds2], 1)))
     out2 = _head(sd, "conv1x1_d2", y)

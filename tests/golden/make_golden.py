@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
 from models.HDenseFormer import HDenseFormer  # noqa: E402  (reference)
+from models.HDenseFormer_2D import HDenseFormer_2D  # noqa: E402  (reference)
 from loss.combine_loss import CEPlusDice, DeepSuperloss  # noqa: E402  (reference)
 from loss.dice_loss import DiceLoss  # noqa: E402
 from loss.cross_entropy import CrossentropyLoss  # noqa: E402
@@ -34,7 +35,8 @@ torch.manual_seed(0)
 
 def model_case(name, in_ch, n_cls, nf, size, td, batch):
     shapes = O.param_shapes(in_ch, n_cls, nf, size, td)
-    ref = HDenseFormer(in_ch, n_cls, nf, image_size=size, transformer_depth=td)
+    cls = HDenseFormer if len(size) == 3 else HDenseFormer_2D
+    ref = cls(in_ch, n_cls, nf, image_size=size, transformer_depth=td)
     ref_sd = ref.state_dict()
     assert list(ref_sd.keys()) == list(shapes.keys()), "state_dict key order/name mismatch"
     for k, v in ref_sd.items():
@@ -103,4 +105,5 @@ def loss_case():
 if __name__ == "__main__":
     model_case("model_nf16_32cube", 2, 3, 16, (32, 32, 32), 4, 1)
     model_case("model_nf8_aniso", 3, 2, 8, (16, 32, 48), 8, 2)
+    model_case("model2d_nf16_64x48", 3, 3, 16, (64, 48), 4, 2)        # HDenseFormer_2D (models/HDenseFormer_2D.py)
     loss_case()

@@ -18,7 +18,7 @@ def _load(golden_dir, name):
     return meta, np.load(os.path.join(golden_dir, name + ".npz"))
 
 
-@pytest.mark.parametrize("name", ["model_nf16_32cube", "model_nf8_aniso"])
+@pytest.mark.parametrize("name", ["model_nf16_32cube", "model_nf8_aniso", "model2d_nf16_64x48"])
 def test_model_forward_backward_matches_reference(golden_dir, name):
     meta, g = _load(golden_dir, name)
     size = tuple(meta["image_size"])
