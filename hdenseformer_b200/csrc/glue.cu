@@ -682,14 +682,15 @@ __global__ void uncast_rows_kernel(const T* __restrict__ src, long long lds, flo
 // 2x2x2 max pool, first maximum in (kd,kh,kw) scan order wins (torch semantics: strict '>' update)
 template <typename T, int VEC>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo, int Do,
-                                   int Ho, int Wo, int C) {
+                                   int Ho, int Wo, int C, int pd) {
+  // pd = pooling window along depth: 2 (MaxPool3d(2)) or 1 (MaxPool2d(2) on a [N, 1, H, W, C] slice, models/HDenseFormer_2D.py)
   const int cpv = C / VEC;
-  const int Hi = 2 * Ho, Wi = 2 * Wo, Di = 2 * Do;
+  const int Hi = 2 * Ho, Wi = 2 * Wo, Di = pd * Do;
   int line = blockIdx.x;
   const int h = line % Ho; line /= Ho;
   const int d = line % Do;
   const long long n = line / Do;
-  const T* xin = x + (((n * Di + 2 * d) * Hi + 2 * h) * (long long)Wi) * ldx;
+  const T* xin = x + (((n * Di + pd * d) * Hi + 2 * h) * (long long)Wi) * ldx;
   T* orow = out + ((long long)blockIdx.x * Wo) * ldo;
   for (int i = threadIdx.x; i < Wo * cpv; i += blockDim.x) {
     const int w = i / cpv, c = (i - w * cpv) * VEC;
@@ -699,9 +700,10 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __
     float v[8][VEC];
 #pragma unroll
     for (int t = 0; t < 8; ++t)
-      loadv<T, VEC>(xin + (((long long)(t >> 2) * Hi + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1)) * ldx + c, v[t]);
+      if ((t >> 2) < pd) loadv<T, VEC>(xin + (((long long)(t >> 2) * Hi + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1)) * ldx + c, v[t]);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
+      if ((t >> 2) >= pd) continue;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) m[k] = (v[t][k] > m[k] || v[t][k] != v[t][k]) ? v[t][k] : m[k];
     }
@@ -712,14 +714,14 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __
 // dx[argmax] (+)= dpool ; other 7 positions get 0 when !accumulate
 template <typename T, int VEC>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ dp, long long ldp,
-                                   T* __restrict__ dx, long long lddx, int Do, int Ho, int Wo, int C, int accumulate) {
+                                   T* __restrict__ dx, long long lddx, int Do, int Ho, int Wo, int C, int accumulate, int pd) {
   const int cpv = C / VEC;
-  const int Hi = 2 * Ho, Wi = 2 * Wo, Di = 2 * Do;
+  const int Hi = 2 * Ho, Wi = 2 * Wo, Di = pd * Do;
   int line = blockIdx.x;
   const int h = line % Ho; line /= Ho;
   const int d = line % Do;
   const long long n = line / Do;
-  const long long row0 = ((n * Di + 2 * d) * Hi + 2 * h) * (long long)Wi;
+  const long long row0 = ((n * Di + pd * d) * Hi + 2 * h) * (long long)Wi;
   const T* prow = dp + ((long long)blockIdx.x * Wo) * ldp;
   for (int i = threadIdx.x; i < Wo * cpv; i += blockDim.x) {
     const int w = i / cpv, c = (i - w * cpv) * VEC;
@@ -732,17 +734,19 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, long long ldx, const
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       rows[t] = row0 + ((long long)(t >> 2) * Hi + ((t >> 1) & 1)) * Wi + 2 * w + (t & 1);
-      loadv<T, VEC>(x + rows[t] * ldx + c, v[t]);
+      if ((t >> 2) < pd) loadv<T, VEC>(x + rows[t] * ldx + c, v[t]);
     }
     loadv<T, VEC>(prow + (long long)w * ldp + c, g);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
+      if ((t >> 2) >= pd) continue;
 #pragma unroll
       for (int k = 0; k < VEC; ++k)
         if (v[t][k] > m[k] || v[t][k] != v[t][k]) { m[k] = v[t][k]; am[k] = t; }
     }
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
+      if ((t >> 2) >= pd) continue;
       float o[VEC];
       if (accumulate) loadv<T, VEC>(dx + rows[t] * lddx + c, o);
 #pragma unroll
@@ -763,16 +767,18 @@ __device__ __forceinline__ void up2_src(int o, int In, int& i0, int& i1, float& 
 
 template <typename T, int VEC>
 __global__ void upsample2_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ out, long long ldo, int Di,
-                                     int Hi, int Wi, int C) {
+                                     int Hi, int Wi, int C, int sd) {
+  // sd = scale along depth: 2 (trilinear) or 1 (bilinear x2 of a [N, 1, H, W, C] slice, models/HDenseFormer_2D.py:171)
   const int cpv = C / VEC;
-  const int Do = 2 * Di, Ho = 2 * Hi, Wo = 2 * Wi;
+  const int Do = sd * Di, Ho = 2 * Hi, Wo = 2 * Wi;
   int line = blockIdx.x;
   const int h = line % Ho; line /= Ho;
   const int d = line % Do;
   const long long n = line / Do;
   int d0, d1, h0, h1;
   float fd, fh;
-  up2_src(d, Di, d0, d1, fd);
+  if (sd == 1) { d0 = d1 = d; fd = 0.f; }
+  else up2_src(d, Di, d0, d1, fd);
   up2_src(h, Hi, h0, h1, fh);
   const T* l00 = x + (((n * Di + d0) * Hi + h0) * (long long)Wi) * ldx;
   const T* l01 = x + (((n * Di + d0) * Hi + h1) * (long long)Wi) * ldx;
@@ -901,16 +907,17 @@ __device__ __forceinline__ void up2_bwd_taps(int i, int In, int* o, float* w) {
 
 template <typename T, int VEC>
 __global__ void upsample2_bwd_kernel(const T* __restrict__ dout, long long ldd, T* __restrict__ dx, long long lddx, int Di,
-                                     int Hi, int Wi, int C, int accumulate) {
+                                     int Hi, int Wi, int C, int accumulate, int sd) {
   const int cpv = C / VEC;
-  const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
+  const int Ho = 2 * Hi, Wo = 2 * Wi, Do = sd * Di;
   int line = blockIdx.x;
   const int h = line % Hi; line /= Hi;
   const int d = line % Di;
   const long long n = line / Di;
   int od[4], oh[4];
   float wd[4], wh[4];
-  up2_bwd_taps(d, Di, od, wd);
+  if (sd == 1) { od[0] = od[1] = od[2] = od[3] = d; wd[0] = wd[2] = wd[3] = 0.f; wd[1] = 1.f; }
+  else up2_bwd_taps(d, Di, od, wd);
   up2_bwd_taps(h, Hi, oh, wh);
   T* xrow = dx + ((long long)blockIdx.x * Wi) * lddx;
   for (int i = threadIdx.x; i < Wi * cpv; i += blockDim.x) {
@@ -1547,49 +1554,63 @@ int hdf_cast_rows_to_f32(int dtype, const void* src, long long lds, float* dst, 
   return HDF_OK;
 }
 
-int hdf_maxpool2_fwd(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Do, int Ho, int Wo,
-                     int C, void* stream) {
-  HDF_REQUIRE(x && out, "hdf_maxpool2_fwd: null pointer");
+// pd = pooling window along depth: 2 = MaxPool3d(2); 1 = MaxPool2d(2) applied to [N, Do, 2Ho, 2Wo, C] slices (flat volumes)
+int hdf_maxpool2_fwd_ex(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Do, int Ho, int Wo,
+                        int C, int pd, void* stream) {
+  HDF_REQUIRE(x && out && (pd == 1 || pd == 2), "hdf_maxpool2_fwd: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(out, ldo, C);
-    HDF_VEC_DISPATCH(vec, { maxpool_fwd_kernel<T, VEC><<<(unsigned)((long long)N * Do * Ho), line_block(Wo * (C / VEC)), 0, s>>>((const T*)x, ldx, (T*)out, ldo, Do, Ho, Wo, C); });
+    HDF_VEC_DISPATCH(vec, { maxpool_fwd_kernel<T, VEC><<<(unsigned)((long long)N * Do * Ho), line_block(Wo * (C / VEC)), 0, s>>>((const T*)x, ldx, (T*)out, ldo, Do, Ho, Wo, C, pd); });
   });
   HDF_LAUNCH_CHECK("hdf_maxpool2_fwd");
   return HDF_OK;
 }
+int hdf_maxpool2_fwd(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Do, int Ho, int Wo,
+                     int C, void* stream) {
+  return hdf_maxpool2_fwd_ex(dtype, x, ldx, out, ldo, N, Do, Ho, Wo, C, 2, stream);
+}
 
-int hdf_maxpool2_bwd(int dtype, const void* x, long long ldx, const void* dpool, long long ldp, void* dx, long long lddx,
-                     int N, int Do, int Ho, int Wo, int C, int accumulate, void* stream) {
-  HDF_REQUIRE(x && dpool && dx, "hdf_maxpool2_bwd: null pointer");
+int hdf_maxpool2_bwd_ex(int dtype, const void* x, long long ldx, const void* dpool, long long ldp, void* dx, long long lddx,
+                        int N, int Do, int Ho, int Wo, int C, int accumulate, int pd, void* stream) {
+  HDF_REQUIRE(x && dpool && dx && (pd == 1 || pd == 2), "hdf_maxpool2_bwd: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(dpool, ldp, C) && can_vec<T>(dx, lddx, C);
-    HDF_VEC_DISPATCH(vec, { maxpool_bwd_kernel<T, VEC><<<(unsigned)((long long)N * Do * Ho), line_block(Wo * (C / VEC)), 0, s>>>((const T*)x, ldx, (const T*)dpool, ldp, (T*)dx, lddx, Do, Ho, Wo, C, accumulate); });
+    HDF_VEC_DISPATCH(vec, { maxpool_bwd_kernel<T, VEC><<<(unsigned)((long long)N * Do * Ho), line_block(Wo * (C / VEC)), 0, s>>>((const T*)x, ldx, (const T*)dpool, ldp, (T*)dx, lddx, Do, Ho, Wo, C, accumulate, pd); });
   });
   HDF_LAUNCH_CHECK("hdf_maxpool2_bwd");
   return HDF_OK;
 }
+int hdf_maxpool2_bwd(int dtype, const void* x, long long ldx, const void* dpool, long long ldp, void* dx, long long lddx,
+                     int N, int Do, int Ho, int Wo, int C, int accumulate, void* stream) {
+  return hdf_maxpool2_bwd_ex(dtype, x, ldx, dpool, ldp, dx, lddx, N, Do, Ho, Wo, C, accumulate, 2, stream);
+}
 
-int hdf_upsample2_fwd(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Di, int Hi, int Wi,
-                      int C, void* stream) {
-  HDF_REQUIRE(x && out, "hdf_upsample2_fwd: null pointer");
+// sd = scale along depth: 2 = trilinear x2; 1 = bilinear x2 of [N, Di, Hi, Wi, C] slices (flat volumes; generic kernel only)
+int hdf_upsample2_fwd_ex(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Di, int Hi, int Wi,
+                         int C, int sd, void* stream) {
+  HDF_REQUIRE(x && out && (sd == 1 || sd == 2), "hdf_upsample2_fwd: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(x, ldx, C) && can_vec<T>(out, ldo, C);
-    if (vec && dtype == HDF_BF16) {
+    if (vec && dtype == HDF_BF16 && sd == 2) {
       upsample2_fwd_cell_kernel<<<(unsigned)((long long)N * (Di + 1) * (Hi + 1)), line_block((Wi + 1) * (C / 8)), 0, s>>>((const bf16*)x, ldx, (bf16*)out, ldo, Di, Hi, Wi, C);
     } else {
-      HDF_VEC_DISPATCH(vec, { upsample2_fwd_kernel<T, VEC><<<(unsigned)((long long)N * Di * Hi * 4), line_block(2 * Wi * (C / VEC)), 0, s>>>((const T*)x, ldx, (T*)out, ldo, Di, Hi, Wi, C); });
+      HDF_VEC_DISPATCH(vec, { upsample2_fwd_kernel<T, VEC><<<(unsigned)((long long)N * Di * sd * Hi * 2), line_block(2 * Wi * (C / VEC)), 0, s>>>((const T*)x, ldx, (T*)out, ldo, Di, Hi, Wi, C, sd); });
     }
   });
   HDF_LAUNCH_CHECK("hdf_upsample2_fwd");
   return HDF_OK;
 }
+int hdf_upsample2_fwd(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Di, int Hi, int Wi,
+                      int C, void* stream) {
+  return hdf_upsample2_fwd_ex(dtype, x, ldx, out, ldo, N, Di, Hi, Wi, C, 2, stream);
+}
 
-int hdf_upsample2_bwd(int dtype, const void* dout, long long ldd, void* dx, long long lddx, int N, int Di, int Hi, int Wi,
-                      int C, int accumulate, void* stream) {
-  HDF_REQUIRE(dout && dx, "hdf_upsample2_bwd: null pointer");
+int hdf_upsample2_bwd_ex(int dtype, const void* dout, long long ldd, void* dx, long long lddx, int N, int Di, int Hi, int Wi,
+                         int C, int accumulate, int sd, void* stream) {
+  HDF_REQUIRE(dout && dx && (sd == 1 || sd == 2), "hdf_upsample2_bwd: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   HDF_DISPATCH_DTYPE(dtype, T, {
     const bool vec = can_vec<T>(dout, ldd, C) && can_vec<T>(dx, lddx, C);
@@ -1597,17 +1618,21 @@ int hdf_upsample2_bwd(int dtype, const void* dout, long long ldd, void* dx, long
     // measured slower than the gather form (0.49 vs 0.30 ms at 144^3: two phases, 18 KB + 99 registers per CTA) -> opt-in
     static const bool ups_v2 = getenv("HDF_UPS_BWD_V2") != nullptr;
     static const bool ups_gather = getenv("HDF_UPS_BWD_GATHER") != nullptr;
-    if (vec && dtype == HDF_BF16 && !ups_gather && !ups_v2) {
+    if (vec && dtype == HDF_BF16 && !ups_gather && !ups_v2 && sd == 2) {
       const int Db = (Di + 1) / 2, Hb = (Hi + 1) / 2;
       upsample2_bwd_blk_kernel<<<(unsigned)((long long)N * Db * Hb), line_block(Wi * (C / 8)), 0, s>>>((const bf16*)dout, ldd, (bf16*)dx, lddx, Di, Hi, Wi, C, accumulate);
-    } else if (vec && dtype == HDF_BF16 && line_smem <= 48 * 1024 && ups_v2) {
+    } else if (vec && dtype == HDF_BF16 && line_smem <= 48 * 1024 && ups_v2 && sd == 2) {
       upsample2_bwd_line_kernel<<<(unsigned)((long long)N * Di * Hi), line_block(2 * Wi * (C / 8)), line_smem, s>>>((const bf16*)dout, ldd, (bf16*)dx, lddx, Di, Hi, Wi, C, accumulate);
     } else {
-      HDF_VEC_DISPATCH(vec, { upsample2_bwd_kernel<T, VEC><<<(unsigned)((long long)N * Di * Hi), line_block(Wi * (C / VEC)), 0, s>>>((const T*)dout, ldd, (T*)dx, lddx, Di, Hi, Wi, C, accumulate); });
+      HDF_VEC_DISPATCH(vec, { upsample2_bwd_kernel<T, VEC><<<(unsigned)((long long)N * Di * Hi), line_block(Wi * (C / VEC)), 0, s>>>((const T*)dout, ldd, (T*)dx, lddx, Di, Hi, Wi, C, accumulate, sd); });
     }
   });
   HDF_LAUNCH_CHECK("hdf_upsample2_bwd");
   return HDF_OK;
+}
+int hdf_upsample2_bwd(int dtype, const void* dout, long long ldd, void* dx, long long lddx, int N, int Di, int Hi, int Wi,
+                      int C, int accumulate, void* stream) {
+  return hdf_upsample2_bwd_ex(dtype, dout, ldd, dx, lddx, N, Di, Hi, Wi, C, accumulate, 2, stream);
 }
 
 int hdf_head_fwd(int dtype, const void* a, long long lda, const float* w, const float* b, void* out, int N, long long V,

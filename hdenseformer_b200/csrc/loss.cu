@@ -12,6 +12,7 @@ constexpr int MAXCLS = 8;
 struct LevelGeom {
   int Dl, Hl, Wl;      // level dims
   int stride;          // 2^level
+  int dstride;         // stride along depth: = stride, or 1 for flat volumes (2-D model: [B, C, 1, H, W])
   long long Vfull;     // full-res voxels per channel
   int Hf, Wf;          // full-res H, W
 };
@@ -21,7 +22,7 @@ __device__ __forceinline__ long long target_index(const LevelGeom& g, long long 
   const long long r = v / g.Wl;
   const int h = r % g.Hl;
   const int d = r / g.Hl;
-  return ((long long)(d * g.stride) * g.Hf + h * g.stride) * g.Wf + w * g.stride;
+  return ((long long)(d * g.dstride) * g.Hf + h * g.stride) * g.Wf + w * g.stride;
 }
 
 // sums layout (double): [B][C][3] = inter, psum, tsum ; then [2] = ce_num, ce_den
@@ -287,14 +288,26 @@ extern "C" {
 size_t hdf_loss_sums_bytes(int B, int C) { return (size_t)(B * C * 3 + 2) * sizeof(double); }
 
 // sums must be zeroed by this call (done here with a memset node on the stream)
+int hdf_loss_level_fwd_ex(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
+                          int Hl, int Wl, int level_stride, int depth_stride, int ignore_index, int has_ignore, float smooth,
+                          float level_weight, float ce_weight, float dice_weight, double* sums, float* out_level, float* total,
+                          void* stream);
 int hdf_loss_level_fwd(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
                        int Hl, int Wl, int level_stride, int ignore_index, int has_ignore, float smooth, float level_weight,
                        float ce_weight, float dice_weight, double* sums, float* out_level, float* total, void* stream) {
+  return hdf_loss_level_fwd_ex(dtype, logits, target, class_weight, B, C, Dl, Hl, Wl, level_stride, level_stride, ignore_index,
+                               has_ignore, smooth, level_weight, ce_weight, dice_weight, sums, out_level, total, stream);
+}
+// depth_stride: stride of the full-resolution target along depth (= level_stride for volumes, 1 for flat [B, C, 1, H, W] inputs)
+int hdf_loss_level_fwd_ex(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
+                          int Hl, int Wl, int level_stride, int depth_stride, int ignore_index, int has_ignore, float smooth,
+                          float level_weight, float ce_weight, float dice_weight, double* sums, float* out_level, float* total,
+                          void* stream) {
   HDF_REQUIRE(logits && target && sums && out_level && total && C >= 1 && C <= MAXCLS,
               "hdf_loss_level_fwd: bad args (n_cls must be 1..%d)", MAXCLS);
   cudaStream_t s = (cudaStream_t)stream;
   const long long V = (long long)Dl * Hl * Wl;
-  LevelGeom g{Dl, Hl, Wl, level_stride, V * level_stride * level_stride * level_stride, Hl * level_stride, Wl * level_stride};
+  LevelGeom g{Dl, Hl, Wl, level_stride, depth_stride, V * depth_stride * level_stride * level_stride, Hl * level_stride, Wl * level_stride};
   cudaError_t e = cudaMemsetAsync(sums, 0, hdf_loss_sums_bytes(B, C), s);
   if (e != cudaSuccess) { hdf_set_error("hdf_loss_level_fwd: memset failed: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
   int chunks = (int)((V + 4095) / 4096);
@@ -312,13 +325,24 @@ int hdf_loss_level_fwd(int dtype, const void* logits, const float* target, const
   return HDF_OK;
 }
 
+int hdf_loss_level_bwd_ex(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
+                          int Hl, int Wl, int level_stride, int depth_stride, int ignore_index, int has_ignore, float smooth,
+                          float level_weight, float ce_weight, float dice_weight, const double* sums, const float* grad_out,
+                          void* dlogits, void* stream);
 int hdf_loss_level_bwd(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
                        int Hl, int Wl, int level_stride, int ignore_index, int has_ignore, float smooth, float level_weight,
                        float ce_weight, float dice_weight, const double* sums, const float* grad_out, void* dlogits,
                        void* stream) {
+  return hdf_loss_level_bwd_ex(dtype, logits, target, class_weight, B, C, Dl, Hl, Wl, level_stride, level_stride, ignore_index,
+                               has_ignore, smooth, level_weight, ce_weight, dice_weight, sums, grad_out, dlogits, stream);
+}
+int hdf_loss_level_bwd_ex(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
+                          int Hl, int Wl, int level_stride, int depth_stride, int ignore_index, int has_ignore, float smooth,
+                          float level_weight, float ce_weight, float dice_weight, const double* sums, const float* grad_out,
+                          void* dlogits, void* stream) {
   HDF_REQUIRE(logits && target && sums && dlogits && C >= 1 && C <= MAXCLS, "hdf_loss_level_bwd: bad args");
   const long long V = (long long)Dl * Hl * Wl;
-  LevelGeom g{Dl, Hl, Wl, level_stride, V * level_stride * level_stride * level_stride, Hl * level_stride, Wl * level_stride};
+  LevelGeom g{Dl, Hl, Wl, level_stride, depth_stride, V * depth_stride * level_stride * level_stride, Hl * level_stride, Wl * level_stride};
   int gx = (int)((V + 255) / 256);
   const int cap = (8 * 148 + B - 1) / B;
   if (gx > cap) gx = cap;

@@ -304,15 +304,16 @@ struct PatchA {
   int D, H, W, M;
   const float* base;
   bool valid;
+  int pdep;          // patch depth: 16 (Conv3d k16) or 1 (Conv2d k16 on a [B, M, 1, H, W] slice: K = 256)
   __device__ void init(int, int m0, int tid) {
     int m = m0 + tid / 4;
     valid = m < M;
-    const int w16 = W / 16, h16 = H / 16, d16 = D / 16;
+    const int w16 = W / 16, h16 = H / 16, d16 = D / pdep;
     const int pw = m % w16; m /= w16;
     const int ph = m % h16; m /= h16;
     const int pd = m % d16;
     const int b = m / d16;
-    base = img + b * batch_stride + ((long long)(pd * 16) * H + ph * 16) * W + pw * 16;
+    base = img + b * batch_stride + ((long long)(pd * pdep) * H + ph * 16) * W + pw * 16;
   }
   __device__ void load4(int, int k, int kend, float* o) const {
     o[0] = o[1] = o[2] = o[3] = 0.f;
@@ -327,18 +328,19 @@ struct PatchAT {
   const float* img;
   long long batch_stride;
   int D, H, W;
+  int pdep;
   __device__ void init(int, int, int) {}
   __device__ void load4(int m, int k, int kend, float* o) const {
     o[0] = o[1] = o[2] = o[3] = 0.f;
     if (k >= kend) return;
-    const int w16 = W / 16, h16 = H / 16, d16 = D / 16;
+    const int w16 = W / 16, h16 = H / 16, d16 = D / pdep;
     int t = k;
     const int pw = t % w16; t /= w16;
     const int ph = t % h16; t /= h16;
     const int pd = t % d16;
     const int b = t / d16;
     const int kw = m & 15, kh = (m >> 4) & 15, kd = m >> 8;
-    ::load4<float>(img + b * batch_stride + ((long long)(pd * 16 + kd) * H + ph * 16 + kh) * W + pw * 16 + kw, o);
+    ::load4<float>(img + b * batch_stride + ((long long)(pd * pdep + kd) * H + ph * 16 + kh) * W + pw * 16 + kw, o);
   }
 };
 
@@ -582,8 +584,11 @@ int hdf_conv3d_wgrad(int dtype, int mode, const void* x, long long ldx, const vo
   return HDF_OK;
 }
 
+// D == 1 selects the 2-D patch embedding (Conv2d k16 s16 of models/HDenseFormer_2D.py:112-115): patch depth 1, K = 256
+static inline int patch_depth(int D) { return D == 1 ? 1 : 16; }
+
 size_t hdf_patch_embed_fwd_workspace(int B, int D, int H, int W, int E) {
-  const long long M = (long long)B * (D / 16) * (H / 16) * (W / 16);
+  const long long M = (long long)B * (D / patch_depth(D)) * (H / 16) * (W / 16);
   return (size_t)8 * M * E * sizeof(float);
 }
 
@@ -595,15 +600,16 @@ int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, i
                         const float* bias, const float* pos, float* out, long long ldo, int E, float p,
                         const unsigned long long* seed_ptr, unsigned long long seed, unsigned call_id, void* workspace,
                         size_t ws_bytes, void* stream) {
-  HDF_REQUIRE(img && weight && out && workspace && (D % 16 == 0) && (H % 16 == 0) && (W % 16 == 0) && (W % 4 == 0),
-              "hdf_patch_embed_fwd: bad args (every spatial dim must be a multiple of 16)");
-  const int ntok = (D / 16) * (H / 16) * (W / 16);
+  const int pdep = patch_depth(D), K = pdep * 256;
+  HDF_REQUIRE(img && weight && out && workspace && (D % pdep == 0) && (H % 16 == 0) && (W % 16 == 0) && (W % 4 == 0),
+              "hdf_patch_embed_fwd: bad args (every spatial dim must be a multiple of 16; depth 1 = 2-D patches)");
+  const int ntok = (D / pdep) * (H / 16) * (W / 16);
   const int M = B * ntok;
   HDF_REQUIRE(ws_bytes >= (size_t)8 * M * E * sizeof(float), "hdf_patch_embed_fwd: workspace too small");
-  PatchA al{img + (long long)modality * D * H * W, (long long)Mch * D * H * W, D, H, W, M, nullptr, false};
-  ColMajorB bl{weight, 4096, E};
+  PatchA al{img + (long long)modality * D * H * W, (long long)Mch * D * H * W, D, H, W, M, nullptr, false, pdep};
+  ColMajorB bl{weight, K, E};
   PartialEp ep{(float*)workspace, 1};
-  int rc = launch_gemm(al, bl, ep, M, E, 4096, 1, 8, (cudaStream_t)stream, "hdf_patch_embed_fwd");
+  int rc = launch_gemm(al, bl, ep, M, E, K, 1, 8, (cudaStream_t)stream, "hdf_patch_embed_fwd");
   if (rc) return rc;
   const long long total = (long long)M * E;
   patch_finish_kernel<<<min(1024, cdiv(total, 256)), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, 8, out, ldo, bias,
@@ -613,12 +619,13 @@ int hdf_patch_embed_fwd(const float* img, int B, int Mch, int modality, int D, i
 }
 
 size_t hdf_patch_embed_wgrad_workspace(int B, int D, int H, int W, int E) {
-  const long long K = (long long)B * (D / 16) * (H / 16) * (W / 16);
-  const int tiles = cdiv(4096, BM) * cdiv(E, BN);
+  const int pk = patch_depth(D) * 256;
+  const long long K = (long long)B * (D / patch_depth(D)) * (H / 16) * (W / 16);
+  const int tiles = cdiv(pk, BM) * cdiv(E, BN);
   int S = (int)((2 * 148 + tiles - 1) / tiles);
   if (S > K) S = (int)K;
   if (S < 1) S = 1;
-  return (size_t)S * 4096 * E * sizeof(float);
+  return (size_t)S * pk * E * sizeof(float);
 }
 
 // dweight[E,4096] (+)= dtok^T @ patches ; dtok [B*ntok, ldd] fp32 (already multiplied by the dropout mask)
@@ -626,24 +633,25 @@ int hdf_patch_embed_wgrad(const float* img, int B, int Mch, int modality, int D,
                           long long ldd, float* dweight, int E, void* workspace, size_t ws_bytes, int accumulate,
                           void* stream) {
   HDF_REQUIRE(img && dtok && dweight && workspace, "hdf_patch_embed_wgrad: null pointer");
-  const int ntok = (D / 16) * (H / 16) * (W / 16);
+  const int pdep = patch_depth(D), pk = pdep * 256;
+  const int ntok = (D / pdep) * (H / 16) * (W / 16);
   const int K = B * ntok;
-  const int tiles = cdiv(4096, BM) * cdiv(E, BN);
+  const int tiles = cdiv(pk, BM) * cdiv(E, BN);
   int S = (2 * 148 + tiles - 1) / tiles;
   if (S > K) S = K;
   if (S < 1) S = 1;
-  HDF_REQUIRE(ws_bytes >= (size_t)S * 4096 * E * sizeof(float), "hdf_patch_embed_wgrad: workspace too small");
+  HDF_REQUIRE(ws_bytes >= (size_t)S * pk * E * sizeof(float), "hdf_patch_embed_wgrad: workspace too small");
   int kps = cdiv(cdiv(K, S), BK) * BK;
   S = cdiv(K, kps);
   // computes P[m = k-in-patch][n = e]; stored transposed into dweight[e][m] by the reducer
-  PatchAT al{img + (long long)modality * D * H * W, (long long)Mch * D * H * W, D, H, W};
+  PatchAT al{img + (long long)modality * D * H * W, (long long)Mch * D * H * W, D, H, W, pdep};
   ActRowsB<float> bl{dtok, ldd, E};
   PartialEp ep{(float*)workspace, 1};
-  int rc = launch_gemm(al, bl, ep, 4096, E, K, 1, S, (cudaStream_t)stream, "hdf_patch_embed_wgrad");
+  int rc = launch_gemm(al, bl, ep, pk, E, K, 1, S, (cudaStream_t)stream, "hdf_patch_embed_wgrad");
   if (rc) return rc;
-  const long long cnt = 4096ll * E;
+  const long long cnt = (long long)pk * E;
   reduce_transpose_kernel<<<min(1024, cdiv(cnt, 256)), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dweight, S,
-                                                                                      4096, E, accumulate);
+                                                                                      pk, E, accumulate);
   HDF_LAUNCH_CHECK("hdf_patch_embed_wgrad/reduce");
   return HDF_OK;
 }

@@ -50,7 +50,10 @@ class Config:
         self.image_size = tuple(image_size)
         self.nblocks = transformer_depth // 4
         self.E = 4 * n_filters
-        self.tok_grid = tuple(s // 16 for s in image_size)
+        # flat = the 2-D model (reference models/HDenseFormer_2D.py) run as [N, 1, H, W, C] volumes: the depth axis is never
+        # pooled / up-sampled / strided, 16 x 16 patches
+        self.flat = self.image_size[0] == 1
+        self.tok_grid = tuple(1 if (self.flat and i == 0) else s // 16 for i, s in enumerate(image_size))
         self.ntok = self.tok_grid[0] * self.tok_grid[1] * self.tok_grid[2]
 
 
@@ -202,12 +205,26 @@ class Engine:
             wp = ops.conv_pack(w, Cin, Cout, 27, Cin * 27, False)
         else:            # ConvTranspose3d weight [Cin, Cout, 27]
             Cin, Cout = w.shape[0], w.shape[1]
+            if out.shape[1] == x.shape[1]:
+                # flat volume (2-D model): ConvTranspose2d = plane 0 of the 3-D transposed conv of the one-plane input when
+                # only the kd = 1 taps are non-zero (out[2j + 0] takes tap kd = 1; the odd plane sees kd = 0 / 2 only)
+                tmp = torch.empty((x.shape[0], 2 * x.shape[1], *out.shape[2:4], Cout), dtype=out.dtype, device=out.device)
+                self._conv_fwd(x, w, bias, tmp, mode=1)
+                out.copy_(tmp[:, ::2])
+                return out
             if self.use_tc and x.dtype == torch.bfloat16 and x.shape[-1] == Cin and ops.tc_convt_supported(Cin, Cout):
                 return ops.tc_convt_fwd(x, self._pack_convt(w), bias, out)
             if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_supported(1, Cin, Cout):
                 return ops.tc_conv3d_fwd(x, self._pack(w, Cin, Cout, Cout * 27, 27, False), bias, out, mode=1)
             wp = ops.conv_pack(w, Cin, Cout, Cout * 27, 27, False)
         return ops.conv3d_fwd(x, wp, bias, out, mode)
+
+    @staticmethod
+    def _lift_depth(t):
+        """[N, D, H, W, C] view of a flat volume -> dense [N, 2D, H, W, C] with the odd planes zero"""
+        z = torch.zeros((t.shape[0], 2 * t.shape[1], *t.shape[2:]), dtype=t.dtype, device=t.device)
+        z[:, ::2].copy_(t)
+        return z
 
     def _conv_dgrad(self, dy, w, out, mode=0):
         """input gradient of _conv_fwd(mode): mode 0 -> conv with flipped taps, swapped channels;
@@ -220,6 +237,8 @@ class Engine:
             wp = ops.conv_pack(w, Cout, Cin, Cin * 27, 27, True)      # packed[tap][co][ci] = w[co][ci][26-tap]
             return ops.conv3d_fwd(dy, wp, None, out, 0)
         Cin, Cout = w.shape[0], w.shape[1]
+        if dy.shape[1] == out.shape[1]:
+            dy = self._lift_depth(dy)          # flat volume: the odd output plane carries no gradient
         if self.use_tc and dy.dtype == torch.bfloat16 and ops.tc_supported(2, Cout, Cin):
             # strided conv over dy: GEMM K = Cout, N = Cin; packed[tap][n=ci][k=co] = w[ci][co][tap]
             return ops.tc_conv3d_fwd(dy, self._pack(w, Cout, Cin, 27, Cout * 27, False), None, out, mode=2)
@@ -242,6 +261,8 @@ class Engine:
             ops.conv3d_wgrad(x, dy, dw, 27, Cin * 27, 0)
         else:            # dw [Cin, Cout, 27]
             Cin, Cout = dw.shape[0], dw.shape[1]
+            if dy.shape[1] == x.shape[1]:
+                dy = self._lift_depth(dy)
             if self.use_tc and x.dtype == torch.bfloat16 and ops.tc_wgrad_supported(1, Cin, Cout):
                 return ops.tc_conv3d_wgrad(x, dy, dw, Cout * 27, 27, 1)
             ops.conv3d_wgrad(x, dy, dw, Cout * 27, 27, 1)
@@ -562,7 +583,7 @@ class Engine:
         # ---------------- up-sampling path of the transformer features (UpConv x4)
         def upconv(name, xin):
             a = self._cnr_fwd(c, name, xin, P, affine=False, bias=True)
-            up = empty((B, 2 * a.shape[1], 2 * a.shape[2], 2 * a.shape[3], a.shape[4]))
+            up = empty((B, (1 if cfg.flat else 2) * a.shape[1], 2 * a.shape[2], 2 * a.shape[3], a.shape[4]))
             return ops.upsample2_fwd(a, up)
 
         attnout = upconv("deep_conv", attnall)
@@ -591,18 +612,19 @@ class Engine:
             xcl = ops.ncdhw_to_cl(x, dtype, pad_to=pad)
         c.xcl = xcl
         cat1 = empty((B, D, H, W, 2 * nf))
-        cat2 = empty((B, D // 2, H // 2, W // 2, 4 * nf))
-        cat3 = empty((B, D // 4, H // 4, W // 4, 8 * nf))
+        dl = (lambda l: D) if cfg.flat else (lambda l: D >> l)      # depth of pyramid level l
+        cat2 = empty((B, dl(1), H // 2, W // 2, 4 * nf))
+        cat3 = empty((B, dl(2), H // 4, W // 4, 8 * nf))
         c.cat1, c.cat2, c.cat3 = cat1, cat2, cat3
         a = self._cnr_fwd(c, "block_1_1_left", xcl, P)
         ds0 = self._cnr_fwd(c, "block_1_2_left", a, P, out=cat1[..., nf:], before_apply=join_at3)
-        p1 = ops.maxpool2_fwd(ds0, empty((B, D // 2, H // 2, W // 2, nf)))
+        p1 = ops.maxpool2_fwd(ds0, empty((B, dl(1), H // 2, W // 2, nf)))
         a = self._cnr_fwd(c, "block_2_1_left", p1, P)
         ds1 = self._cnr_fwd(c, "block_2_2_left", a, P, out=cat2[..., 2 * nf:], residual=at2)
-        p2 = ops.maxpool2_fwd(ds1, empty((B, D // 4, H // 4, W // 4, 2 * nf)))
+        p2 = ops.maxpool2_fwd(ds1, empty((B, dl(2), H // 4, W // 4, 2 * nf)))
         a = self._cnr_fwd(c, "block_3_1_left", p2, P)
         ds2 = self._cnr_fwd(c, "block_3_2_left", a, P, out=cat3[..., 4 * nf:], residual=at1)
-        p3 = ops.maxpool2_fwd(ds2, empty((B, D // 8, H // 8, W // 8, 4 * nf)))
+        p3 = ops.maxpool2_fwd(ds2, empty((B, dl(3), H // 8, W // 8, 4 * nf)))
         a = self._cnr_fwd(c, "block_4_1_left", p3, P)
         x4 = self._cnr_fwd(c, "block_4_2_left", a, P, residual=attnout)
         c.x4 = x4
@@ -656,6 +678,7 @@ class Engine:
             return da
 
         D, H, W = cfg.image_size
+        dl = (lambda l: D) if cfg.flat else (lambda l: D >> l)
         self._deferred = []
         self._defer_open = self.use_side_stream and self.defer_wgrad   # only useful with a side branch to overlap
         self._early_left = self.wgrad_early if self._defer_open else 0
@@ -666,21 +689,21 @@ class Engine:
         dA = self._cnr_bwd(c, "block_1_2_right", dA, P, G)
         dcat1 = self._cnr_bwd(c, "block_1_1_right", dA, P, G)
         dA = convt_bwd("upconv_1", dcat1[..., :nf], c.a22)
-        head_bwd("conv1x1_d1", gout(1, (B, cfg.n_cls, D // 2, H // 2, W // 2)), c.a22, dA, True)
+        head_bwd("conv1x1_d1", gout(1, (B, cfg.n_cls, dl(1), H // 2, W // 2)), c.a22, dA, True)
         if not self._defer_open:
             notify("conv1x1_d1.bias")
         # ---- level 1
         dA = self._cnr_bwd(c, "block_2_2_right", dA, P, G)
         dcat2 = self._cnr_bwd(c, "block_2_1_right", dA, P, G)
         dA = convt_bwd("upconv_2", dcat2[..., :2 * nf], c.a32)
-        head_bwd("conv1x1_d2", gout(2, (B, cfg.n_cls, D // 4, H // 4, W // 4)), c.a32, dA, True)
+        head_bwd("conv1x1_d2", gout(2, (B, cfg.n_cls, dl(2), H // 4, W // 4)), c.a32, dA, True)
         if not self._defer_open:
             notify("conv1x1_d2.bias")
         # ---- level 2
         dA = self._cnr_bwd(c, "block_3_2_right", dA, P, G)
         dcat3 = self._cnr_bwd(c, "block_3_1_right", dA, P, G)
         dx4 = convt_bwd("upconv_3", dcat3[..., :4 * nf], c.x4)
-        head_bwd("conv1x1_d3", gout(3, (B, cfg.n_cls, D // 8, H // 8, W // 8)), c.x4, dx4, True)
+        head_bwd("conv1x1_d3", gout(3, (B, cfg.n_cls, dl(3), H // 8, W // 8)), c.x4, dx4, True)
         if not self._defer_open:
             notify("conv1x1_d3.bias")
         # ---- bottleneck + encoder (dx4 is also the gradient of attnout through the residual add)

@@ -86,9 +86,12 @@ def seg_loss(preds, target, weight=None, ignore_index=None, smooth=1e-5, ce_w=1.
     n = len(preds)
     level_weights = level_weights or [1.0] * n
     levels = levels or [0] * n
+    if target.dim() == 4:       # 2-D model (models/HDenseFormer_2D.py): [B, C, H, W] -> flat volumes [B, C, 1, H, W]
+        target = target.unsqueeze(2)
+        preds = [p.unsqueeze(2) for p in preds]
     D, H, W = target.shape[2:]
     for p, lv in zip(preds, levels):
-        exp = (target.shape[0], target.shape[1], D >> lv, H >> lv, W >> lv)
+        exp = (target.shape[0], target.shape[1], D if D == 1 else D >> lv, H >> lv, W >> lv)
         assert tuple(p.shape) == exp, f"predict {tuple(p.shape)} vs target level {lv} {exp}"
     return _SegLossFn.apply(target, weight, ignore_index, float(smooth), float(ce_w), float(dice_w), list(level_weights),
                             list(levels), *preds)

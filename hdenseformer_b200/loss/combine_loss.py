@@ -34,9 +34,10 @@ class DeepSuperloss(nn.Module):
         if isinstance(c, CEPlusDice):
             full = target.shape[2:]
             levels = []
+            nd = len(full)          # 3 (volumes) or 2 (slices of the 2-D model)
             for img in input:
-                lv = [full[d] // img.shape[2 + d] for d in range(3)]
-                ok = lv[0] == lv[1] == lv[2] and lv[0] & (lv[0] - 1) == 0 and all(img.shape[2 + d] * lv[0] == full[d] for d in range(3))
+                lv = [full[d] // img.shape[2 + d] for d in range(nd)]
+                ok = len(set(lv)) == 1 and lv[0] & (lv[0] - 1) == 0 and all(img.shape[2 + d] * lv[0] == full[d] for d in range(nd))
                 levels.append(lv[0].bit_length() - 1 if ok else None)
             if all(l is not None for l in levels):
                 return seg_loss(list(input), target, c.weight, c.ignore_index, _check_kwargs(c.kwargs),

@@ -317,29 +317,40 @@ def cast_to_f32(src: torch.Tensor, dst: torch.Tensor):
              "cast_to_f32")
 
 
+def _depth_factor(d_small: int, d_big: int) -> int:
+    """2 for the 3-D ops, 1 when the depth axis is left alone (flat [N, 1, H, W, C] volumes of the 2-D model)"""
+    f = d_big // max(d_small, 1)
+    assert f in (1, 2) and d_small * f == d_big, f"depth {d_big} vs {d_small}"
+    return f
+
+
 def maxpool2_fwd(x: torch.Tensor, out: torch.Tensor):
     N, Do, Ho, Wo, C = out.shape
-    _C.check(_lib().hdf_maxpool2_fwd(_DT[x.dtype], _p(x), _ld(x), _p(out), _ld(out), N, Do, Ho, Wo, C, _s()), "maxpool2_fwd")
+    pd = _depth_factor(Do, x.shape[1])
+    _C.check(_lib().hdf_maxpool2_fwd_ex(_DT[x.dtype], _p(x), _ld(x), _p(out), _ld(out), N, Do, Ho, Wo, C, pd, _s()), "maxpool2_fwd")
     return out
 
 
 def maxpool2_bwd(x: torch.Tensor, dpool: torch.Tensor, dx: torch.Tensor, accumulate: bool):
     N, Do, Ho, Wo, C = dpool.shape
-    _C.check(_lib().hdf_maxpool2_bwd(_DT[x.dtype], _p(x), _ld(x), _p(dpool), _ld(dpool), _p(dx), _ld(dx), N, Do, Ho, Wo, C,
-                                     int(accumulate), _s()), "maxpool2_bwd")
+    pd = _depth_factor(Do, x.shape[1])
+    _C.check(_lib().hdf_maxpool2_bwd_ex(_DT[x.dtype], _p(x), _ld(x), _p(dpool), _ld(dpool), _p(dx), _ld(dx), N, Do, Ho, Wo, C,
+                                        int(accumulate), pd, _s()), "maxpool2_bwd")
     return dx
 
 
 def upsample2_fwd(x: torch.Tensor, out: torch.Tensor):
     N, Di, Hi, Wi, C = x.shape
-    _C.check(_lib().hdf_upsample2_fwd(_DT[x.dtype], _p(x), _ld(x), _p(out), _ld(out), N, Di, Hi, Wi, C, _s()), "upsample2_fwd")
+    sd = _depth_factor(Di, out.shape[1])
+    _C.check(_lib().hdf_upsample2_fwd_ex(_DT[x.dtype], _p(x), _ld(x), _p(out), _ld(out), N, Di, Hi, Wi, C, sd, _s()), "upsample2_fwd")
     return out
 
 
 def upsample2_bwd(dout: torch.Tensor, dx: torch.Tensor, accumulate: bool = False):
     N, Di, Hi, Wi, C = dx.shape
-    _C.check(_lib().hdf_upsample2_bwd(_DT[dx.dtype], _p(dout), _ld(dout), _p(dx), _ld(dx), N, Di, Hi, Wi, C, int(accumulate),
-                                      _s()), "upsample2_bwd")
+    sd = _depth_factor(Di, dout.shape[1])
+    _C.check(_lib().hdf_upsample2_bwd_ex(_DT[dx.dtype], _p(dout), _ld(dout), _p(dx), _ld(dx), N, Di, Hi, Wi, C, int(accumulate),
+                                         sd, _s()), "upsample2_bwd")
     return dx
 
 
@@ -557,7 +568,7 @@ def patch_embed_fwd(img, modality, weight, bias, pos, out, p, seed, call_id, ten
     path): tcgen05 implicit GEMM with bf16 operands (csrc/patch_tc.cu), else the fp32 SIMT GEMM."""
     B, Mch, D, H, W = img.shape
     E = weight.shape[0]
-    if tensor_cores and _lib().hdf_patch_embed_tc_supported(E):
+    if tensor_cores and D != 1 and _lib().hdf_patch_embed_tc_supported(E):      # D == 1: 2-D patches (K = 256), SIMT path
         ws = Workspace.get(_lib().hdf_patch_embed_tc_workspace(B, D, H, W, E))
         _C.check(_lib().hdf_patch_embed_tc_fwd(_p(img), B, Mch, modality, D, H, W, _p(weight), _p(bias), _p(pos), _p(out),
                                                out.stride(0), E, float(p), *_seed_args(seed), call_id, _p(ws), ws.numel(), _s()),
@@ -585,9 +596,10 @@ def posemb_grad(dtok, dpos, B, ntok, E, accumulate=False):
 def loss_level_fwd(logits, target, cw, level, ignore_index, smooth, level_weight, ce_w, dice_w, sums, out_level, total):
     B, Cc, Dl, Hl, Wl = logits.shape
     has_ig = ignore_index is not None
-    _C.check(_lib().hdf_loss_level_fwd(_DT[logits.dtype], _p(logits), _p(target), _p(cw), B, Cc, Dl, Hl, Wl, 1 << level,
-                                       ignore_index if has_ig else -1, int(has_ig), smooth, level_weight, ce_w, dice_w,
-                                       _p(sums), _p(out_level), _p(total), _s()), "loss_level_fwd")
+    ds = 1 if target.shape[2] == Dl else 1 << level          # flat inputs (2-D model): the depth axis is not strided
+    _C.check(_lib().hdf_loss_level_fwd_ex(_DT[logits.dtype], _p(logits), _p(target), _p(cw), B, Cc, Dl, Hl, Wl, 1 << level, ds,
+                                          ignore_index if has_ig else -1, int(has_ig), smooth, level_weight, ce_w, dice_w,
+                                          _p(sums), _p(out_level), _p(total), _s()), "loss_level_fwd")
 
 
 def confusion_update(logits: torch.Tensor, target: torch.Tensor, conf: torch.Tensor):
@@ -602,9 +614,10 @@ def confusion_update(logits: torch.Tensor, target: torch.Tensor, conf: torch.Ten
 def loss_level_bwd(logits, target, cw, level, ignore_index, smooth, level_weight, ce_w, dice_w, sums, grad_out, dlogits):
     B, Cc, Dl, Hl, Wl = logits.shape
     has_ig = ignore_index is not None
-    _C.check(_lib().hdf_loss_level_bwd(_DT[logits.dtype], _p(logits), _p(target), _p(cw), B, Cc, Dl, Hl, Wl, 1 << level,
-                                       ignore_index if has_ig else -1, int(has_ig), smooth, level_weight, ce_w, dice_w,
-                                       _p(sums), _p(grad_out), _p(dlogits), _s()), "loss_level_bwd")
+    ds = 1 if target.shape[2] == Dl else 1 << level
+    _C.check(_lib().hdf_loss_level_bwd_ex(_DT[logits.dtype], _p(logits), _p(target), _p(cw), B, Cc, Dl, Hl, Wl, 1 << level, ds,
+                                          ignore_index if has_ig else -1, int(has_ig), smooth, level_weight, ce_w, dice_w,
+                                          _p(sums), _p(grad_out), _p(dlogits), _s()), "loss_level_bwd")
 
 
 def sw_accumulate(logits, agg, x0, y0, z0):

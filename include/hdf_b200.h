@@ -234,6 +234,16 @@ int hdf_upsample2_fwd(int dtype, const void* x, long long ldx, void* out, long l
                       int C, void* stream);
 int hdf_upsample2_bwd(int dtype, const void* dout, long long ldd, void* dx, long long lddx, int N, int Di, int Hi, int Wi,
                       int C, int accumulate, void* stream);
+/* the same four entries with an explicit depth factor for FLAT volumes [N, 1, H, W, C] (the 2-D model,
+ * reference models/HDenseFormer_2D.py: MaxPool2d(2), bilinear x2): pd / sd = 1 leaves the depth axis alone, 2 = the 3-D op */
+int hdf_maxpool2_fwd_ex(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Do, int Ho, int Wo,
+                        int C, int pd, void* stream);
+int hdf_maxpool2_bwd_ex(int dtype, const void* x, long long ldx, const void* dpool, long long ldp, void* dx, long long lddx,
+                        int N, int Do, int Ho, int Wo, int C, int accumulate, int pd, void* stream);
+int hdf_upsample2_fwd_ex(int dtype, const void* x, long long ldx, void* out, long long ldo, int N, int Di, int Hi, int Wi,
+                         int C, int sd, void* stream);
+int hdf_upsample2_bwd_ex(int dtype, const void* dout, long long ldd, void* dx, long long lddx, int N, int Di, int Hi, int Wi,
+                         int C, int accumulate, int sd, void* stream);
 int hdf_add_(int dtype, void* dst, long long ldd, const void* src, long long lds, long long rows, int C, void* stream);
 int hdf_copy_rows(int dtype, void* dst, long long ldd, const void* src, long long lds, long long rows, int C, void* stream);
 int hdf_cast_rows_from_f32(int dtype, const float* src, long long lds, void* dst, long long ldd, long long rows, int C,
@@ -261,6 +271,15 @@ int hdf_loss_level_bwd(int dtype, const void* logits, const float* target, const
                        int Hl, int Wl, int level_stride, int ignore_index, int has_ignore, float smooth, float level_weight,
                        float ce_weight, float dice_weight, const double* sums, const float* grad_out, void* dlogits,
                        void* stream);
+/* ... with a separate stride along depth for flat inputs (2-D model: logits [B, C, 1, H_l, W_l], target [B, C, 1, H, W]) */
+int hdf_loss_level_fwd_ex(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
+                          int Hl, int Wl, int level_stride, int depth_stride, int ignore_index, int has_ignore, float smooth,
+                          float level_weight, float ce_weight, float dice_weight, double* sums, float* out_level, float* total,
+                          void* stream);
+int hdf_loss_level_bwd_ex(int dtype, const void* logits, const float* target, const float* class_weight, int B, int C, int Dl,
+                          int Hl, int Wl, int level_stride, int depth_stride, int ignore_index, int has_ignore, float smooth,
+                          float level_weight, float ce_weight, float dice_weight, const double* sums, const float* grad_out,
+                          void* dlogits, void* stream);
 
 /* ---- sliding-window inference (trainer.py:560-582; cal_steps :595-618 stays host code).
  *      steps_* are HOST arrays of window starts; the count map is analytic, never stored. ---- */

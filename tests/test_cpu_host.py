@@ -145,3 +145,24 @@ def test_fused_adam_and_stem_have_no_cpu_path_and_pure_helpers_answer_without_a_
     m = HDenseFormer(2, 2, 8, (32, 32, 32), 4)
     with pytest.raises(RuntimeError):
         FusedAdam(m, lr=1e-3)
+
+
+def test_2d_model_state_dict_matches_the_reference_module_table():
+    """HDenseFormer_2D: keys / shapes / parameter count of the reference's 2-D module (golden meta written by
+    tests/golden/make_golden.py from models/HDenseFormer_2D.py); construction needs no GPU, forward refuses the CPU."""
+    import json
+    import os
+    import pytest
+    import torch
+    from hdenseformer_b200.models import HDenseFormer_2D, HDenseFormer_2D_16
+    meta = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "model2d_nf16_64x48.json")))
+    m = HDenseFormer_2D(meta["in_channels"], meta["n_cls"], meta["n_filters"], tuple(meta["image_size"]), meta["transformer_depth"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(meta["shapes"].keys())
+    assert all(list(v.shape) == meta["shapes"][k] for k, v in sd.items())
+    assert sum(v.numel() for v in sd.values()) == meta["n_params"]
+    assert HDenseFormer_2D_16(3, 2, (64, 64), 4).n_filters == 16
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 48))
+    with pytest.raises(ValueError):
+        HDenseFormer_2D(3, 2, 16, (60, 48), 4)
