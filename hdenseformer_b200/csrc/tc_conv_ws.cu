@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_conv_ws_kernel(const __grid_
         uint32_t accflag = 0;
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
+          // one-plane volumes (the 2-D model run as flat volumes): planes z-1 and z+1 are the zero padding, their taps add nothing
+          if (p.D == 1 && kd != 1) continue;
           if (kd == 2 && t + 1 < nd) {
             // The barrier round trips of the NEXT tile (its newest plane, its accumulator) are taken here, while the
             // tensor core still works through the MMAs queued above: the issuing thread runs in lockstep with the
