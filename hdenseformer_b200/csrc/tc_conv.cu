@@ -962,6 +962,23 @@ void build_taps_fold(TcTaps& t) {
   }
 }
 
+// one-plane volumes (D == 1: the 2-D model run as flat volumes): the taps of the planes above / below read nothing but
+// zero padding -> keep only the entries with dd == 0 (a third of the boxes and MMAs)
+void filter_taps_flat(TcTaps& t) {
+  TcTaps o;
+  memset(&o, 0, sizeof(o));
+  o.ncls = t.ncls;
+  int n = 0;
+  for (int c = 0; c < t.ncls; ++c) {
+    o.first[c] = (signed char)n;
+    o.pd[c] = t.pd[c]; o.ph[c] = t.ph[c]; o.pw[c] = t.pw[c];
+    for (int e = t.first[c]; e < t.first[c + 1]; ++e)
+      if (t.dd[e] == 0) { o.dd[n] = 0; o.dh[n] = t.dh[e]; o.dw[n] = t.dw[e]; o.widx[n] = t.widx[e]; ++n; }
+  }
+  o.first[t.ncls] = (signed char)n;
+  t = o;
+}
+
 void build_taps(int mode, TcTaps& t) {
   memset(&t, 0, sizeof(t));
   if (mode == 0 || mode == 2) {
@@ -1194,6 +1211,8 @@ static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void
     }
     if (p.fold) build_taps_fold(p.taps);
   }
+  const bool flat = mode == 0 && D == 1;
+  if (flat) filter_taps_flat(p.taps);
   p.num_tiles = p.taps.ncls * N * p.nTd * p.nTh * p.nTw;
   p.b_bytes = (uint32_t)p.Nmma * p.KC * 2u;
   p.b_region = (p.b_bytes + 1023u) & ~1023u;
@@ -1212,7 +1231,7 @@ static int tc_conv_fwd_launch(int mode, const void* x, long long ldx, const void
   p.khfold = 0;
   p.line_bytes = (uint32_t)p.TW * p.KC * 2u;
   static const char* no_kh = getenv("HDF_TC_NO_KHFOLD");
-  if (p.fold && p.b_resident && !no_kh) {
+  if (p.fold && p.b_resident && !no_kh && !flat) {
     // kh-fold: one box of TH+2 lines per kd; needs all lines of the tile in one d-plane
     const int lines = 128 / p.TW;
     p.khfold = 1;

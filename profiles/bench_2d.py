@@ -46,8 +46,19 @@ def main():
     for _ in range(3):
         step()
     ms = timed(step, 5)
-    out = {"what": f"HDenseFormer_2D_32({M},{C},{size},td={td}) train step, batch {B}, bf16, eager launches", "ms_per_step": ms,
-           "slices_per_s": B / (ms / 1e3)}
+    out = {"what": f"HDenseFormer_2D_32({M},{C},{size},td={td}) train step, batch {B}, bf16", "eager_launches": {"ms_per_step": ms,
+           "slices_per_s": B / (ms / 1e3)}}
+    try:
+        from hdenseformer_b200 import trainer as T
+        gopt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True, capturable=True)
+        gs = T.GraphedTrainStep(net, crit, gopt, x, t, use_bf16=True)
+        for _ in range(2):
+            gs.step(x, t)
+        gms = timed(lambda: gs.step(x, t), 10)
+        out["cuda_graph_replay"] = {"ms_per_step": gms, "slices_per_s": B / (gms / 1e3), "loss": float(gs.loss.item())}
+        del gs, gopt
+    except Exception as e:
+        out["cuda_graph_replay"] = {"unavailable": repr(e)[:300]}
     try:
         from oracle import stage_ref
         import importlib
