@@ -534,7 +534,6 @@ __global__ void __launch_bounds__(256) in_bwd_apply_fast_kernel(const T* __restr
   }
 }
 
-// rows per block for the fast elementwise kernels: ~8 resident-CTA waves over the 148 SMs, >= 4 passes of the block
 // InstanceNorm apply + affine + ReLU fused with the 1x1x1 head that reads its output (models/HDenseFormer.py:253-255: the four
 // deep-supervision heads read the outputs of block_k_2_right / block_4_2_left): the head's dot products are taken from the
 // registers that hold the (bf16-rounded) output row, so the head does not read the 2 x 191 MB activation again.  Thread =
@@ -618,6 +617,7 @@ __global__ void __launch_bounds__(256) in_apply_head_kernel(const bf16* __restri
   }
 }
 
+// rows per block for the fast elementwise kernels: ~8 resident-CTA waves over the 148 SMs, >= 4 passes of the block
 inline int fast_rows_per_block(long long V, int N, int rpi) {
   long long target = (148ll * 16 + N - 1) / N;
   long long rpb = (V + target - 1) / target;

@@ -123,6 +123,7 @@ tc_wgrad_ws_kernel(const __grid_constant__ CUtensorMap tmp, const __grid_constan
     const uint64_t adesc_hi = umma_desc(0, p.p_box_bytes, 512, 4);
     const uint64_t bdesc_hi = umma_desc(0, p.line_bytes, 512, 4);
     const int ksteps = p.K / 16;
+    const bool flat = p.D == 1;
     uint32_t ps = 0, pph = 0;
     uint32_t s0 = 0, ws = 0, wph = 0;
     int ahead = 0;
@@ -146,9 +147,11 @@ tc_wgrad_ws_kernel(const __grid_constant__ CUtensorMap tmp, const __grid_constan
         uint64_t b1 = bdesc_hi | (uint64_t)(((q_base + s1 * p.q_slot_bytes) >> 4) & 0x3FFF);
         uint64_t b2 = bdesc_hi | (uint64_t)(((q_base + s2 * p.q_slot_bytes) >> 4) & 0x3FFF);
         for (int k = 0; k < ksteps; ++k) {       // 16 voxel rows = 1024 B per step in every sub-tile
-          umma_ss_p(tmem_base + 0u, ad, b0, idesc, accflag, issue);
+          // one-plane volumes (the 2-D model as flat volumes): planes d-1 / d+1 are zero padding, their taps are written as
+          // zeros by the epilogue instead of being accumulated
+          if (!flat) umma_ss_p(tmem_base + 0u, ad, b0, idesc, accflag, issue);
           umma_ss_p(tmem_base + 96u, ad, b1, idesc, accflag, issue);
-          umma_ss_p(tmem_base + 192u, ad, b2, idesc, accflag, issue);
+          if (!flat) umma_ss_p(tmem_base + 192u, ad, b2, idesc, accflag, issue);
           accflag = 1;
           ad += 64; b0 += 64; b1 += 64; b2 += 64;
         }
@@ -193,6 +196,10 @@ tc_wgrad_ws_kernel(const __grid_constant__ CUtensorMap tmp, const __grid_constan
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                          : "r"(taddr + (uint32_t)c0));
             tmem_ld_wait();
+            if (p.D == 1 && sd != 1) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = 0u;
+            }
             *reinterpret_cast<float4*>(dst + c0) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
             *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
           }

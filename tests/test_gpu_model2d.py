@@ -143,3 +143,37 @@ def test_2d_train_steps_reduce_loss_and_dropout_runs():
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_2d_graphed_train_step_matches_eager():
+    """trainer.GraphedTrainStep is generic: the 2-D module with a capturable torch Adam, dropout off (eval-mode statistics are
+    not involved: InstanceNorm has none), replayed steps == eager steps on the same data."""
+    from hdenseformer_b200 import trainer as T
+    size = (64, 48)
+    shapes = O.param_shapes(3, 2, 16, size, 4)
+    sd = O.synth_state_dict(shapes, seed=11)
+    x = O.synth_mr(2, 3, size, seed=6).to(DEV)
+    tgt = O.synth_label(2, 2, size, seed=6).to(DEV)
+    crit = DeepSuperloss(CEPlusDice(weight=None, ignore_index=0))
+    losses = {}
+    for mode in ("eager", "graph"):
+        m = HDenseFormer_2D(3, 2, 16, size, 4)
+        m.load_state_dict(sd)
+        m = m.to(DEV).eval()                 # eval: no dropout, so both runs see the same arithmetic
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
+        out = []
+        if mode == "graph":
+            gs = T.GraphedTrainStep(m, crit, opt, x, tgt, use_bf16=False, warmup=1)     # one eager step, then the capture
+            out = [float(gs.step(x, tgt).item()) for _ in range(3)]
+        else:
+            for i in range(4):
+                o = m(x)
+                loss = crit(o, tgt)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                if i > 0:
+                    out.append(float(loss.item()))
+        losses[mode] = out
+    assert losses["eager"][-1] < losses["eager"][0]
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(losses["eager"], losses["graph"])), losses
