@@ -561,7 +561,8 @@ struct TcWgradParams {
   int CWn, nsub_b;
   int a_stages;
   int a_scale;             // 1: A-side coords j + (k-1); 2: A-side is the 2x-resolution tensor, coords 2j + (k-1)
-  int ntaps;               // 27, or 1 for the stem's im2col'ed operand (a single unshifted "tap")
+  int ntaps;               // 27, or 1 for the stem's im2col'ed operand (a single unshifted "tap"), or 9 with tap0 = 9 for one-plane volumes
+  int tap0;                // first tap of the processed range (0; 9 = the kd = 1 plane when D == 1: the other planes only see padding)
   uint32_t a_sub_bytes, a_stage_bytes, b_sub_bytes, b_stage_bytes;
   uint32_t a_layout, a_sbo, b_layout, b_sbo;
   uint32_t tmem_cols;
@@ -625,7 +626,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
         if (++bs == 2) { bs = 0; bph ^= 1u; }
         // sub-tile u = g*SPG + j  ->  (tap, channel chunk), tracked incrementally (no per-load divisions)
         int tap = (g_begin * p.SPG) / p.sub_per_tap, sub = (g_begin * p.SPG) - tap * p.sub_per_tap;
-        int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+        int kd = (tap + p.tap0) / 9, kh = (tap / 3) % 3, kw = tap % 3;
         for (int g = g_begin; g < g_end; ++g) {
           const int u0 = g * p.SPG;
           const int nsub = min(p.SPG, p.total_sub - u0);
@@ -903,14 +904,14 @@ tc_conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tms, const __grid_cons
 
 // partials [S][27][Cin][Cout] -> g[ci*sci + co*sco + tap] (+= if accumulate); fixed summation order
 __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ g, int S, int Cin, int Cout,
-                                       long long sci, long long sco, int accumulate, int flip) {
-  const long long per = 27ll * Cin * Cout;
+                                       long long sci, long long sco, int accumulate, int flip, int ntaps = 27, int tap0 = 0) {
+  const long long per = (long long)ntaps * Cin * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < S; ++z) s += part[z * per + i];
     const int co = i % Cout;
     const int ci = (i / Cout) % Cin;
-    const int tap = i / ((long long)Cin * Cout);
+    const int tap = tap0 + (int)(i / ((long long)Cin * Cout));
     float* q = g + ci * sci + co * sco + (flip ? 26 - tap : tap);
     *q = accumulate ? (*q + s) : s;
   }
@@ -1349,6 +1350,7 @@ static int wgrad_target_ctas(int Cin, int Cout) {
 static int tc_wgrad_plan(int N, int D, int H, int W, int Cin, int Cout, TcWgradParams& p, int ntaps = 27) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.ntaps = ntaps;
+  p.tap0 = 0;
   p.a_scale = 1;
   static const int kv_cfg = getenv("HDF_TC_WGRAD_KV") ? atoi(getenv("HDF_TC_WGRAD_KV")) : 0;
   p.KV = (Cout > 128) ? 64 : 128;
@@ -1550,8 +1552,9 @@ size_t hdf_tc_wgrad_workspace(int mode, int N, int Do, int Ho, int Wo, int Cin, 
     return (size_t)q.num_slabs * 27 * Cin * Cout * sizeof(float);
   }
   TcWgradParams p;
-  if (mode == 0 && !wgrad_swap_roles(mode, Cin, Cout)) tc_wgrad_plan(N, Do, Ho, Wo, Cin, Cout, p);
-  else if (mode == 0) tc_wgrad_plan(N, Do, Ho, Wo, Cout, Cin, p);
+  const int ntaps = (mode == 0 && Do == 1) ? 9 : 27;      // one-plane volumes: the kd = 1 taps only (same plan as the launch)
+  if (mode == 0 && !wgrad_swap_roles(mode, Cin, Cout)) tc_wgrad_plan(N, Do, Ho, Wo, Cin, Cout, p, ntaps);
+  else if (mode == 0) tc_wgrad_plan(N, Do, Ho, Wo, Cout, Cin, p, ntaps);
   else tc_wgrad_plan(N, Do / 2, Ho / 2, Wo / 2, Cout, Cin, p);
   return (size_t)p.num_slabs * 27 * Cin * Cout * sizeof(float);
 }
@@ -1586,7 +1589,10 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
   const int Ca = a_is_x ? Cin : Cout, Cb = a_is_x ? Cout : Cin;
   const long long sa = a_is_x ? stride_ci : stride_co, sb = a_is_x ? stride_co : stride_ci;
   TcWgradParams p;
-  const int passes = tc_wgrad_plan(N, D, H, W, Ca, Cb, p);
+  // one-plane volumes (the 2-D model as flat volumes): only the kd = 1 taps see anything but zero padding
+  const bool flat = mode == 0 && D == 1;
+  const int passes = tc_wgrad_plan(N, D, H, W, Ca, Cb, p, flat ? 9 : 27);
+  if (flat) p.tap0 = 9;
   p.a_scale = mode == 0 ? 1 : 2;
   HDF_REQUIRE(ws_bytes >= (size_t)p.num_slabs * 27 * Cin * Cout * sizeof(float), "hdf_tc_conv3d_wgrad: workspace too small");
   p.partial = (float*)workspace;
@@ -1623,9 +1629,15 @@ int hdf_tc_conv3d_wgrad(int mode, const void* x, long long ldx, const void* dy, 
   dim3 grid(p.num_slabs, passes);
   tc_conv_wgrad_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmx, tmdy, p);
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad");
-  const long long per = 27ll * Cin * Cout;
+  if (flat && !accumulate) {
+    // the 18 taps of the two padding planes are exactly zero (stride-1 conv weights are one dense [Cout][Cin][27] block)
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)27 * Cin * Cout * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) { hdf_set_error("hdf_tc_conv3d_wgrad: memset failed: %s", cudaGetErrorString(e)); return HDF_ERR_CUDA; }
+  }
+  const long long per = (long long)p.ntaps * Cin * Cout;
   tc_wgrad_reduce_kernel<<<min(2048, cdiv(per, 256)), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, p.num_slabs,
-                                                                                     Ca, Cb, sa, sb, accumulate, swap ? 1 : 0);
+                                                                                     Ca, Cb, sa, sb, accumulate, swap ? 1 : 0,
+                                                                                     p.ntaps, p.tap0);
   HDF_LAUNCH_CHECK("hdf_tc_conv3d_wgrad/reduce");
   return HDF_OK;
 }
