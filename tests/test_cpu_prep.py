@@ -89,3 +89,28 @@ def test_unsupported_orders_fail_loudly():
         DU.MRNormalize()(s)                                  # two normalisations
     with pytest.raises(ValueError):
         DU.RandomCrop3D((4, 4, 4))({"image": np.zeros((8, 8), np.float32), "label": lab})
+
+
+def test_data_generator_roi_selection_and_plan_recording():
+    """DataGenerator (data_loader.py:162-210) on in-memory samples: ROI selection as in the reference (single ROI -> binary
+    label; list of ROIs -> 1..n), transforms only record (no GPU needed until To_Tensor), samples are not mutated."""
+    from hdenseformer_b200 import data_utils as DU
+    from hdenseformer_b200.data_utils._plan import plan_of
+    rng = np.random.default_rng(0)
+    img = rng.normal(size=(2, 12, 16, 20)).astype(np.float32)
+    lab = rng.integers(0, 4, size=(12, 16, 20)).astype(np.float32)
+    items = [{"image": img, "label": lab}]
+    ds = DU.DataGenerator(items, roi_number=2, num_class=2,
+                          transform=DU.Compose([DU.RandomCrop3D((8, 16, 10)), DU.PETandCTNormalize(), DU.RandomFlip3D("v")]))
+    random.seed(3); np.random.seed(3)
+    s = ds[0]
+    assert np.array_equal(s["label"], (lab == 2).astype(np.float32))
+    p = plan_of(s)
+    assert p.size == (8, 16, 10) and p.origin[1] == 0 and 0 <= p.origin[0] <= 4 and 0 <= p.origin[2] <= 10
+    assert p.norm == "petct" and (p.p0, p.p1) == (0.0, 1024.0) and p.flip_axis == 2 and p.affine is None
+    ds2 = DU.DataGenerator(items, roi_number=[3, 1], num_class=3, transform=None)
+    l2 = ds2[0]["label"]
+    assert np.array_equal(l2 == 1, lab == 3) and np.array_equal(l2 == 2, lab == 1) and set(np.unique(l2)) <= {0.0, 1.0, 2.0}
+    assert np.array_equal(items[0]["label"], lab)               # the stored sample is untouched
+    with pytest.raises(ImportError):
+        DU.hdf5_reader("/nonexistent.hdf5", "ct")                # h5py is not in this image: loud, not silent
