@@ -130,6 +130,16 @@ class DataGenerator(torch.utils.data.Dataset):
     def __len__(self):
         return len(self.path_list)
 
+    def _select_roi(self, label):
+        """one ROI id -> binary mask; a list of ids -> classes 1..n in list order (everything else background)"""
+        rois = self.roi_number if isinstance(self.roi_number, list) else [self.roi_number]
+        assert self.num_class == len(rois) + 1
+        is_t = isinstance(label, torch.Tensor)
+        out = torch.zeros_like(label, dtype=torch.float32) if is_t else np.zeros(label.shape, dtype=np.float32)
+        for cls, roi in enumerate(rois, start=1):
+            out[label == roi] = cls
+        return out
+
     def __getitem__(self, index):
         item = self.path_list[index]
         if isinstance(item, dict):
@@ -138,16 +148,7 @@ class DataGenerator(torch.utils.data.Dataset):
             image = hdf5_reader(item, self.img_key)
             label = hdf5_reader(item, self.lab_key)
         if self.roi_number is not None:
-            xp = torch if isinstance(label, torch.Tensor) else np
-            if isinstance(self.roi_number, list):
-                assert self.num_class == len(self.roi_number) + 1
-                tmp = xp.zeros_like(label)
-                for i, roi in enumerate(self.roi_number):
-                    tmp[label == roi] = i + 1
-                label = tmp
-            else:
-                assert self.num_class == 2
-                label = (label == self.roi_number).float() if xp is torch else (label == self.roi_number).astype(np.float32)
+            label = self._select_roi(label)
         sample = {'image': image, 'label': label}
         if self.transform is not None:
             sample = self.transform(sample)

@@ -51,22 +51,14 @@ class RandomTranslationRotationZoom3D(object):
 
     def __call__(self, sample):
         plan = plan_of(sample)
-        # draw order of the reference: translation (2), rotation (1), zoom (2)
-        if 't' in self.mode:
-            translation = [0, np.random.uniform(-5, 5), np.random.uniform(-5, 5)]
-        else:
-            translation = [0, 0, 0]
-        if 'r' in self.mode:
-            rotation = _rot_x(np.random.uniform(-5, 5) / 180.0 * np.pi)
-        else:
-            rotation = _rot_x(0.0)
-        if 'z' in self.mode:
-            zoom = [1, np.random.uniform(0.9, 1.1), np.random.uniform(0.9, 1.1)]
-        else:
-            zoom = [1, 1, 1]
-        warp_mat = np.eye(4)                     # transforms3d.affines.compose(T, R, Z)
-        warp_mat[:3, :3] = np.dot(rotation, np.diag(zoom))
-        warp_mat[:3, 3] = translation
+        u = np.random.uniform
+        # same draws, same order as the reference: translation (2 uniforms), rotation (1), zoom (2); absent letters draw nothing
+        shift = [0.0, u(-5, 5), u(-5, 5)] if 't' in self.mode else [0.0, 0.0, 0.0]
+        angle = u(-5, 5) / 180.0 * np.pi if 'r' in self.mode else 0.0
+        scale = [1.0, u(0.9, 1.1), u(0.9, 1.1)] if 'z' in self.mode else [1.0, 1.0, 1.0]
+        warp_mat = np.eye(4)                     # transforms3d.affines.compose(T, R, Z) = [[R diag(Z), T], [0, 1]]
+        warp_mat[:3, :3] = _rot_x(angle) @ np.diag(scale)
+        warp_mat[:3, 3] = shift
         plan.warp(warp_mat, self.num_class)
         return sample
 
@@ -78,14 +70,8 @@ class RandomFlip3D(object):
         self.mode = mode
 
     def __call__(self, sample):
-        plan = plan_of(sample)
-        if 'h' in self.mode and 'v' in self.mode:
-            axis = 1 if np.random.uniform(0, 1) > 0.5 else 2
-        elif 'h' in self.mode:
-            axis = 1
-        elif 'v' in self.mode:
-            axis = 2
-        else:
-            axis = 0
-        plan.flip(axis)
+        h, v = 'h' in self.mode, 'v' in self.mode
+        # 'hv': one uniform decides between the H flip (> 0.5) and the W flip; a single letter always flips its axis
+        axis = (1 if np.random.uniform(0, 1) > 0.5 else 2) if (h and v) else (1 if h else 2 if v else 0)
+        plan_of(sample).flip(axis)
         return sample
